@@ -1,0 +1,171 @@
+/*
+ * mmvid_b200 - C ABI of the B200-native MMVID token-generation hot path.
+ *
+ * The reference (snap-research/MMVID) has NO operator / FFI boundary: every FLOP is a stock PyTorch call
+ * made from three Python classes.  This header therefore *defines* the boundary the
+ * replacement exports; each entry point cites the reference code whose compute it replaces.  The Python
+ * classes in mmvid_b200/ (same names, signatures and state-dict keys as the reference's BERT / DALLE /
+ * VQGanVAE1024 / OpenAICLIPTransformer) call these through ctypes with raw device pointers.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; pointers are DEVICE pointers unless named host_*;
+ *   - no allocation, no ownership transfer: outputs / scratch are caller-allocated;
+ *   - stream-ordered on `stream` (a cudaStream_t); re-entrant across streams; safe to capture in CUDA graphs;
+ *   - return 0 on success, negative MMVID_E* otherwise; mmvid_last_error() gives a thread-local message;
+ *   - activations are fp32 unless a dtype argument says otherwise; `precision` selects the math pipe:
+ *       MMVID_FP32  CUDA-core FFMA, fp32 accumulate  (parity / bit-exact-index mode)
+ *       MMVID_TF32  tcgen05.mma kind::tf32, fp32 accumulate in TMEM (<=1e-3 logits parity mode)
+ *       MMVID_BF16  tcgen05.mma kind::f16 (bf16 operands), fp32 accumulate in TMEM (throughput mode)
+ */
+#ifndef MMVID_B200_H
+#define MMVID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mmvid_stream_t; /* cudaStream_t */
+
+enum { MMVID_OK = 0, MMVID_EINVAL = -1, MMVID_ECUDA = -2, MMVID_EUNSUPPORTED = -3 };
+enum { MMVID_FP32 = 0, MMVID_TF32 = 1, MMVID_BF16 = 2 };
+enum { MMVID_ACT_NONE = 0, MMVID_ACT_QUICKGELU = 1, MMVID_ACT_SWISH = 2 };
+enum { MMVID_MASK_NONE = 0, MMVID_MASK_CAUSAL = 1, MMVID_MASK_PREV = 2 };
+enum { MMVID_DT_F32 = 0, MMVID_DT_BF16 = 1 };
+
+int mmvid_version(void);
+const char* mmvid_last_error(void);
+/* number of kernels this library has launched since load / last reset (bench.py "gpu_launches") */
+long long mmvid_launch_count(void);
+void mmvid_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  fused token + positional embedding gather  (reference: dalle_bert.py:903-972,1032-1036;
+ *     dalle_artv.py:441-491: ~7 nn.Embedding gathers + adds + torch.cat)
+ * Writes rows [seq_off, seq_off+n) of the residual stream out[B, S, D]:
+ *     id = ids[b*ids_bstride + i];  if (id == pad_value) id = pad_base + i;      (unique pad ids, :917-919)
+ *     out[b, seq_off+i, :] = table[id, :] + (pos ? pos[i, :] : 0) + (table2 ? table2[id, :] : 0)
+ * ids: int64.  table2 covers special_emb + special_pos_emb indexed by the same id (:903-906).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const int64_t* ids; long long ids_bstride; int n; int seq_off;
+  const float* table; const float* table2; const float* pos;
+  long long pad_value; long long pad_base; int use_pad;
+} mmvid_embed_segment;
+int mmvid_embed_gather(float* out, int B, int S, int D, const mmvid_embed_segment* host_segments, int num_segments,
+                       mmvid_stream_t stream);
+
+/* axial positional table: out[i, :] = sum_a w_a[coord_a(i), :], i < n  (axial_positional_embedding, summed
+ * in axis order ((w0 + w1) + w2) like the package's python sum()).  shape[] = axis lengths (naxes <= 3). */
+int mmvid_axial_table(float* out, int n, int D, const float* w0, const float* w1, const float* w2,
+                      const int* host_shape, int naxes, mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  LayerNorm over the last dim (clip_model.py:188-193 eps 1e-5; to_logits.0 dalle_bert.py:414-425)
+ *     out dtype fp32 or bf16 (bf16 feeds the kind::f16 GEMMs).  x row stride = ldx elements.
+ * ---------------------------------------------------------------------------------------------- */
+int mmvid_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, void* out, int out_dtype,
+                    long long rows, int D, float eps, mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3/K5/K6/K7  Linear:  C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N])
+ *     (F.linear inside nn.MultiheadAttention in/out-proj clip_model.py:208,222; mlp c_fc/c_proj :210-213;
+ *      to_logits.1 dalle_bert.py:416; 1x1 convs model.py:124,159-178, vqgan.py:41-43)
+ * a_dtype / w_dtype: MMVID_DT_F32 or MMVID_DT_BF16 (bf16 only with MMVID_BF16).  c_dtype likewise.
+ * All leading dimensions in elements.  residual may alias C.
+ * ---------------------------------------------------------------------------------------------- */
+int mmvid_linear(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
+                 const float* bias, const float* residual, long long ldr, void* C, int c_dtype, long long ldc,
+                 long long M, int N, int K, int act, int precision, mmvid_stream_t stream);
+
+/* Strided-batched fp32 GEMM on CUDA cores (parity path of attention / spatial attention):
+ *   C[b1,b2][m,n] = alpha * sum_k A[b1,b2][m,k] * B[b1,b2](k,n),   B(k,n) at  B + n*ldb_n + k*ldb_k */
+int mmvid_gemm_batched_f32(const float* A, long long lda, long long a_s1, long long a_s2,
+                           const float* B, long long ldb_n, long long ldb_k, long long b_s1, long long b_s2,
+                           float* C, long long ldc, long long c_s1, long long c_s2,
+                           int M, int N, int K, int batch1, int batch2, float alpha, mmvid_stream_t stream);
+
+/* In-place masked row softmax of scores[batch, rows, cols] (fp32 path of F.scaled_dot_product_attention /
+ * AttnBlock softmax model.py:193): mask CAUSAL: col <= row; MASK_PREV: rows listed in prev_rows (device int32,
+ * n_prev of them) see only cols >= row (clip_model.py:571-575); others see everything. */
+int mmvid_softmax_rows(float* scores, long long batch, int rows, int cols, long long ld, int mask_kind,
+                       const int* prev_rows, int n_prev, mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3-K5  multi-head attention core on tensor cores (F.scaled_dot_product_attention, clip_model.py:219-222):
+ *   out[b, s, h*64:(h+1)*64] = softmax(Q K^T / 8 + mask) V        head_dim fixed at 64 (CLIP)
+ *   q, k: [B, H, S_pad, 64]; vt: [B, H, 64, S_pad] (V transposed; produced by mmvid_linear's QKV epilogue
+ *   via mmvid_qkv_split); S_pad = S rounded up to 128.  dtype fp32 (TF32) or bf16 (BF16).
+ * ---------------------------------------------------------------------------------------------- */
+int mmvid_attention(const void* q, const void* k, const void* vt, void* out, int out_dtype, long long ldo,
+                    int B, int H, int S, int S_pad, int mask_kind, const int* host_prev_rows, int n_prev,
+                    int precision, mmvid_stream_t stream);
+/* qkv [B*S, 3*H*64] fp32 -> q,k [B,H,S_pad,64], vt [B,H,64,S_pad] in fp32 or bf16 (zero padded) */
+int mmvid_qkv_split(const float* qkv, void* q, void* k, void* vt, int dtype, int B, int H, int S, int S_pad,
+                    mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9  ART-V KV-cache decode (new capability; the reference re-runs the full prefix, dalle_artv.py:258-281)
+ *   single-query attention against cached K/V: q [B,H,64], kcache/vcache [B,H,S_max,64], len = #valid keys
+ * ---------------------------------------------------------------------------------------------- */
+int mmvid_decode_attention(const float* q, long long q_bstride, const float* kcache, const float* vcache,
+                           float* out, long long o_bstride, int B, int H, int S_max, int len, mmvid_stream_t stream);
+/* GEMV-style linear for tiny M (decode): C[M,N] = act(A[M,K].W[N,K]^T + bias) (+ residual); M <= 16 */
+int mmvid_linear_small_m(const float* A, long long lda, const float* W, long long ldw, const float* bias,
+                         const float* residual, long long ldr, float* C, long long ldc, int M, int N, int K, int act,
+                         mmvid_stream_t stream);
+/* append k,v rows of qkv[B, 3*H*64] into the caches at position pos */
+int mmvid_kv_append(const float* qkv, long long qkv_bstride, float* kcache, float* vcache, int B, int H, int S_max,
+                    int pos, mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K14  VQ nearest-codeword lookup (taming/modules/vqvae/quantize.py:302-311):
+ *   d[t,j] = (sum z_t^2 + sum e_j^2) - 2 z_t.e_j   in fp32, this association; idx[t] = argmin_j (lowest index wins)
+ *   z: [T, dim] (NHWC rows); codebook [n_codes, dim]; idx int64 [T]
+ * ---------------------------------------------------------------------------------------------- */
+int mmvid_vq_argmin(const float* z, const float* codebook, int64_t* idx, long long T, int n_codes, int dim,
+                    mmvid_stream_t stream);
+
+/* K15 codebook gather for decode (vae.py:50-52): out[t, :] = codebook[ids[t], :]  (NHWC rows) */
+int mmvid_codebook_gather(const int64_t* ids, const float* codebook, float* out, long long T, int dim,
+                          mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K10/K13  Conv2d on NHWC fp32 activations (taming/modules/diffusionmodules/model.py:102-115 etc.)
+ *   w packed [Cout, KH, KW, Cin].  out[n,y,x,co] = bias[co] + sum in[n, y*stride+ky-pad_t, x*stride+kx-pad_l, ci] w
+ *   (+ residual[n,y,x,co]).  upsample=1: input is read through a nearest x2 upsample (Upsample, model.py:56-62).
+ *   Downsample (model.py:77-84) = stride 2, pad_t=pad_l=0 with zero fill beyond the right/bottom edge.
+ *   in_nchw / out_nchw: read / write NCHW instead (first / last layer of the VQGAN; fuses vae.py:41 `2x-1`
+ *   when pre_affine=1 and vae.py:55 clamp(-1,1)*0.5+0.5 when post_clamp=1).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* in; const float* w; const float* bias; const float* residual; float* out;
+  int N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, upsample;
+  int in_nchw, out_nchw, pre_affine, post_clamp, precision;
+} mmvid_conv_params;
+int mmvid_conv2d(const mmvid_conv_params* p, mmvid_stream_t stream);
+
+/* K11 GroupNorm(32 groups, eps) + optional swish on NHWC (model.py:38-42, 33-35):
+ *   stats scratch: float [N*32*2].  out may alias in. */
+int mmvid_groupnorm(const float* in, float* out, const float* gamma, const float* beta, float* stats_scratch,
+                    int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream);
+
+/* nearest x2 upsample NHWC (used only when not fused into the conv) */
+int mmvid_upsample2x(const float* in, float* out, int N, int H, int W, int C, mmvid_stream_t stream);
+
+/* elementwise helpers: NCHW<->NHWC transposes of small tensors */
+int mmvid_nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, mmvid_stream_t stream);
+int mmvid_nhwc_to_nchw(const float* in, float* out, int N, int C, int HW, mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7/K8 sampling support: row softmax of logits [rows, n] -> probs (fp32), optional additive noise
+ * (dalle_bert.py:527-531 `logits + temperature * gumbel`), temperature applied by caller via noise scale */
+int mmvid_softmax_logits(const float* logits, const float* noise, float noise_scale, float* probs, long long rows,
+                         int n, mmvid_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMVID_B200_H */

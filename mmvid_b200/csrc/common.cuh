@@ -1,0 +1,86 @@
+// Shared host/device helpers for libmmvid_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/mmvid_b200.h"
+
+namespace mmvid {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// check the launch we just made (does not synchronise)
+inline int check_launch(const char* what) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return MMVID_ECUDA;
+  }
+  return MMVID_OK;
+}
+
+#define MMVID_REQUIRE(cond, msg)                                              \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      snprintf(::mmvid::g_err, sizeof(::mmvid::g_err), "%s: requirement failed: %s (%s)", __func__, #cond, msg); \
+      return MMVID_EINVAL;                                                    \
+    }                                                                         \
+  } while (0)
+
+static inline cudaStream_t to_stream(mmvid_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (all threads get the result)
+__device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  float r = (lane < nw) ? smem[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  float r = (lane < nw) ? smem[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == MMVID_ACT_QUICKGELU) return v / (1.f + expf(-1.702f * v));   // x*sigmoid(1.702x), clip_model.py:196
+  if (act == MMVID_ACT_SWISH) return v / (1.f + expf(-v));                // x*sigmoid(x), model.py:33
+  return v;
+}
+
+}  // namespace mmvid

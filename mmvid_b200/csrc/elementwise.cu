@@ -1,0 +1,506 @@
+// HBM-bound kernels of the MMVID hot path: embedding gather (K1), LayerNorm (K2), row softmax,
+// QKV split/transposes, GroupNorm+swish (K11), VQ argmin (K14), codebook gather (K15), layout helpers.
+// All are coalesced along the channel (innermost) dimension with 128-bit accesses where alignment allows.
+#include "common.cuh"
+
+namespace mmvid {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+}  // namespace mmvid
+
+using namespace mmvid;
+
+extern "C" int mmvid_version(void) { return 100; }
+extern "C" const char* mmvid_last_error(void) { return g_err; }
+extern "C" long long mmvid_launch_count(void) { return g_launches.load(); }
+extern "C" void mmvid_reset_launch_count(void) { g_launches.store(0); }
+
+// ------------------------------------------------------------------------------------------------
+// K1 embedding gather: one warp-group row per block row; segments in constant-size param array.
+// ------------------------------------------------------------------------------------------------
+#define MMVID_MAX_SEGMENTS 8
+struct EmbedParams {
+  mmvid_embed_segment seg[MMVID_MAX_SEGMENTS];
+  int nseg;
+};
+
+__global__ void embed_gather_kernel(float* __restrict__ out, int S, int D, EmbedParams p) {
+  // grid.x = covered rows of one batch element (sum of seg.n), grid.y = B
+  int r = blockIdx.x;
+  const int b = blockIdx.y;
+  int s = 0;
+  while (s < p.nseg - 1 && r >= p.seg[s].n) { r -= p.seg[s].n; ++s; }
+  const mmvid_embed_segment& g = p.seg[s];
+  long long id = g.ids[(long long)b * g.ids_bstride + r];
+  if (g.use_pad && id == g.pad_value) id = g.pad_base + r;
+  const float4* t = reinterpret_cast<const float4*>(g.table + id * (long long)D);
+  const float4* t2 = g.table2 ? reinterpret_cast<const float4*>(g.table2 + id * (long long)D) : nullptr;
+  const float4* ps = g.pos ? reinterpret_cast<const float4*>(g.pos + (long long)r * D) : nullptr;
+  float4* o = reinterpret_cast<float4*>(out + ((long long)b * S + g.seq_off + r) * D);
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    float4 v = __ldg(t + c);
+    if (t2) { float4 w = __ldg(t2 + c); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    if (ps) { float4 w = __ldg(ps + c); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    o[c] = v;
+  }
+}
+
+extern "C" int mmvid_embed_gather(float* out, int B, int S, int D, const mmvid_embed_segment* segs, int nseg,
+                                  mmvid_stream_t stream) {
+  MMVID_REQUIRE(nseg >= 1 && nseg <= MMVID_MAX_SEGMENTS, "1..8 segments");
+  MMVID_REQUIRE(D % 4 == 0, "D must be a multiple of 4");
+  EmbedParams p;
+  p.nseg = nseg;
+  int rows = 0;
+  for (int i = 0; i < nseg; ++i) {
+    p.seg[i] = segs[i];
+    MMVID_REQUIRE(segs[i].n > 0 && segs[i].seq_off >= 0 && segs[i].seq_off + segs[i].n <= S, "segment range");
+    rows += segs[i].n;
+  }
+  if (B == 0) return MMVID_OK;
+  embed_gather_kernel<<<dim3(rows, B), 192, 0, to_stream(stream)>>>(out, S, D, p);
+  return check_launch("embed_gather");
+}
+
+__global__ void axial_table_kernel(float* __restrict__ out, int n, int D, const float* __restrict__ w0,
+                                   const float* __restrict__ w1, const float* __restrict__ w2, int s0, int s1,
+                                   int s2, int naxes) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  int c2 = 0, c1 = 0, c0 = 0;
+  if (naxes == 3) { c2 = i % s2; c1 = (i / s2) % s1; c0 = i / (s2 * s1); }
+  else if (naxes == 2) { c1 = i % s1; c0 = i / s1; }
+  else { c0 = i; }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v = w0[(long long)c0 * D + c];                 // python sum(): ((0 + e0) + e1) + e2
+    if (naxes >= 2) v = v + w1[(long long)c1 * D + c];
+    if (naxes >= 3) v = v + w2[(long long)c2 * D + c];
+    out[(long long)i * D + c] = v;
+  }
+}
+
+extern "C" int mmvid_axial_table(float* out, int n, int D, const float* w0, const float* w1, const float* w2,
+                                 const int* shape, int naxes, mmvid_stream_t stream) {
+  MMVID_REQUIRE(naxes >= 1 && naxes <= 3, "1..3 axes");
+  int s0 = shape[0], s1 = naxes > 1 ? shape[1] : 1, s2 = naxes > 2 ? shape[2] : 1;
+  MMVID_REQUIRE(n <= s0 * s1 * s2, "n exceeds axial volume");
+  axial_table_kernel<<<n, 256, 0, to_stream(stream)>>>(out, n, D, w0, w1, w2, s0, s1, s2, naxes);
+  return check_launch("axial_table");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 LayerNorm: one warp per row when D <= 1024 (row kept in registers: one HBM read, one write).
+// Two-pass (mean, then centered variance) in fp32 like ATen's CPU/CUDA kernels.
+// ------------------------------------------------------------------------------------------------
+template <int VEC_PER_LANE, typename OutT>
+__global__ void layernorm_warp_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, OutT* __restrict__ out, long long rows, int D,
+                                      float eps) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const int nvec = D >> 2;
+  float4 v[VEC_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) { v[i] = xr[c]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(OutT) == 4) {
+        reinterpret_cast<float4*>(out + row * (long long)D)[c] = o;
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(out + row * (long long)D)[c] = pk;
+      }
+    }
+  }
+}
+
+extern "C" int mmvid_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
+                               int out_dtype, long long rows, int D, float eps, mmvid_stream_t stream) {
+  MMVID_REQUIRE(D % 4 == 0 && D <= 1024 && ldx % 4 == 0, "D multiple of 4, <= 1024");
+  if (rows == 0) return MMVID_OK;
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div<long long>(rows, wpb));
+  cudaStream_t st = to_stream(stream);
+  if (out_dtype == MMVID_DT_F32)
+    layernorm_warp_kernel<8, float><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (float*)out, rows, D, eps);
+  else
+    layernorm_warp_kernel<8, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__nv_bfloat16*)out, rows,
+                                                                      D, eps);
+  return check_launch("layernorm");
+}
+
+// ------------------------------------------------------------------------------------------------
+// masked row softmax (fp32 parity path of SDPA / AttnBlock).  One block per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(float* __restrict__ s, int rows, int cols, long long ld, int mask_kind,
+                                    const int* __restrict__ prev_rows, int n_prev) {
+  __shared__ float red[32];
+  const long long r_all = blockIdx.x;
+  const int row = (int)(r_all % rows);
+  float* p = s + r_all * ld;
+  int lo = 0, hi = cols;  // visible columns [lo, hi)
+  if (mask_kind == MMVID_MASK_CAUSAL) hi = min(cols, row + 1);
+  else if (mask_kind == MMVID_MASK_PREV) {
+    for (int i = 0; i < n_prev; ++i) if (prev_rows[i] == row) lo = row;
+  }
+  float m = -INFINITY;
+  for (int c = lo + threadIdx.x; c < hi; c += blockDim.x) m = fmaxf(m, p[c]);
+  m = block_max(m, red);
+  float sum = 0.f;
+  for (int c = lo + threadIdx.x; c < hi; c += blockDim.x) { float e = expf(p[c] - m); p[c] = e; sum += e; }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) p[c] = (c >= lo && c < hi) ? p[c] * inv : 0.f;
+}
+
+extern "C" int mmvid_softmax_rows(float* scores, long long batch, int rows, int cols, long long ld, int mask_kind,
+                                  const int* prev_rows, int n_prev, mmvid_stream_t stream) {
+  if (batch * rows == 0) return MMVID_OK;
+  MMVID_REQUIRE(batch * rows < (1ll << 31), "too many rows");
+  softmax_rows_kernel<<<(unsigned)(batch * rows), 256, 0, to_stream(stream)>>>(scores, rows, cols, ld, mask_kind,
+                                                                                 prev_rows, n_prev);
+  return check_launch("softmax_rows");
+}
+
+// logits -> probs with optional additive noise (sampling head, dalle_bert.py:527-531)
+__global__ void softmax_logits_kernel(const float* __restrict__ logits, const float* __restrict__ noise,
+                                      float noise_scale, float* __restrict__ probs, int n) {
+  __shared__ float red[32];
+  const long long r = blockIdx.x;
+  const float* l = logits + r * n;
+  const float* z = noise ? noise + r * n : nullptr;
+  float* p = probs + r * n;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    float v = l[c];
+    if (z) v = v + noise_scale * z[c];
+    p[c] = v;
+    m = fmaxf(m, v);
+  }
+  m = block_max(m, red);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) { float e = expf(p[c] - m); p[c] = e; sum += e; }
+  sum = block_sum(sum, red);
+  for (int c = threadIdx.x; c < n; c += blockDim.x) p[c] = p[c] / sum;
+}
+
+extern "C" int mmvid_softmax_logits(const float* logits, const float* noise, float noise_scale, float* probs,
+                                    long long rows, int n, mmvid_stream_t stream) {
+  if (rows == 0) return MMVID_OK;
+  softmax_logits_kernel<<<(unsigned)rows, 256, 0, to_stream(stream)>>>(logits, noise, noise_scale, probs, n);
+  return check_launch("softmax_logits");
+}
+
+// ------------------------------------------------------------------------------------------------
+// qkv [B*S, 3*H*64] -> q,k [B,H,S_pad,64]  vt [B,H,64,S_pad]   (zero padded rows)
+// block = 64 tokens x one head; V is transposed through shared memory so both sides stay coalesced.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void qkv_split_kernel(const float* __restrict__ qkv, T* __restrict__ q, T* __restrict__ k,
+                                 T* __restrict__ vt, int H, int S, int S_pad) {
+  __shared__ float tile[64][65];
+  const int s0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int D3 = 3 * H * 64, D = H * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 64 x 4
+  const long long head = ((long long)b * H + h);
+  for (int r = ty; r < 64; r += 4) {
+    const int s = s0 + r;
+    float vq = 0.f, vk = 0.f, vv = 0.f;
+    if (s < S) {
+      const float* row = qkv + ((long long)b * S + s) * D3 + h * 64 + tx;
+      vq = row[0]; vk = row[D]; vv = row[2 * D];
+    }
+    q[(head * S_pad + s) * 64 + tx] = cvt_out<T>(vq);
+    k[(head * S_pad + s) * 64 + tx] = cvt_out<T>(vk);
+    tile[r][tx] = vv;
+  }
+  __syncthreads();
+  for (int d = ty; d < 64; d += 4) vt[(head * 64 + d) * S_pad + s0 + tx] = cvt_out<T>(tile[tx][d]);
+}
+
+extern "C" int mmvid_qkv_split(const float* qkv, void* q, void* k, void* vt, int dtype, int B, int H, int S, int S_pad,
+                               mmvid_stream_t stream) {
+  MMVID_REQUIRE(S_pad % 64 == 0 && S_pad >= S, "S_pad multiple of 64");
+  dim3 grid(S_pad / 64, H, B);
+  if (dtype == MMVID_DT_F32)
+    qkv_split_kernel<float><<<grid, 256, 0, to_stream(stream)>>>(qkv, (float*)q, (float*)k, (float*)vt, H, S, S_pad);
+  else
+    qkv_split_kernel<__nv_bfloat16><<<grid, 256, 0, to_stream(stream)>>>(qkv, (__nv_bfloat16*)q, (__nv_bfloat16*)k,
+                                                                        (__nv_bfloat16*)vt, H, S, S_pad);
+  return check_launch("qkv_split");
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW <-> NHWC (32x32 smem tile transpose), nearest upsample
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cn) {
+  // in [batch, R, Cn] -> out [batch, Cn, R]
+  __shared__ float t[32][33];
+  const long long base = (long long)blockIdx.z * R * Cn;
+  int r = blockIdx.y * 32 + threadIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = 0; i < 32; i += 8)
+    if (r + i < R && c < Cn) t[threadIdx.y + i][threadIdx.x] = in[base + (long long)(r + i) * Cn + c];
+  __syncthreads();
+  r = blockIdx.y * 32 + threadIdx.x; c = blockIdx.x * 32 + threadIdx.y;
+  for (int i = 0; i < 32; i += 8)
+    if (c + i < Cn && r < R) out[base + (long long)(c + i) * R + r] = t[threadIdx.x][threadIdx.y + i];
+}
+
+extern "C" int mmvid_nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, mmvid_stream_t stream) {
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N);
+  transpose_kernel<<<grid, dim3(32, 8), 0, to_stream(stream)>>>(in, out, C, HW);
+  return check_launch("nchw_to_nhwc");
+}
+extern "C" int mmvid_nhwc_to_nchw(const float* in, float* out, int N, int C, int HW, mmvid_stream_t stream) {
+  dim3 grid(ceil_div(C, 32), ceil_div(HW, 32), N);
+  transpose_kernel<<<grid, dim3(32, 8), 0, to_stream(stream)>>>(in, out, HW, C);
+  return check_launch("nhwc_to_nchw");
+}
+
+__global__ void upsample2x_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4,
+                                  long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long p = i / C4;
+    const int x = (int)(p % (2 * W)); p /= (2 * W);
+    const int y = (int)(p % (2 * H));
+    const long long n = p / (2 * H);
+    out[i] = in[((n * H + (y >> 1)) * W + (x >> 1)) * C4 + c];
+  }
+}
+extern "C" int mmvid_upsample2x(const float* in, float* out, int N, int H, int W, int C, mmvid_stream_t stream) {
+  MMVID_REQUIRE(C % 4 == 0, "C multiple of 4");
+  const long long total = (long long)N * 4 * H * W * (C / 4);
+  const int blocks = (int)std::min<long long>(ceil_div<long long>(total, 256), 148 * 16);
+  upsample2x_kernel<<<blocks, 256, 0, to_stream(stream)>>>((const float4*)in, (float4*)out, H, W, C / 4, total);
+  return check_launch("upsample2x");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11 GroupNorm(+swish) on NHWC.  Pass 1: per-(n, group) mean / rstd (one block each, two-pass over
+// the group's HW x (C/G) elements, float accumulation of centered squares).  Pass 2: elementwise apply.
+// ------------------------------------------------------------------------------------------------
+__global__ void groupnorm_stats_kernel(const float* __restrict__ in, float* __restrict__ stats, int HW, int C,
+                                       int G, float eps) {
+  __shared__ float red[32];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int cpg = C / G;
+  const float* base = in + (long long)n * HW * C + g * cpg;
+  const long long cnt = (long long)HW * cpg;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const long long p = i / cpg; const int c = (int)(i % cpg);
+    s += base[p * C + c];
+  }
+  const float mean = block_sum(s, red) / (float)cnt;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const long long p = i / cpg; const int c = (int)(i % cpg);
+    const float d = base[p * C + c] - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, red) / (float)cnt;
+  if (threadIdx.x == 0) {
+    stats[((long long)n * G + g) * 2 + 0] = mean;
+    stats[((long long)n * G + g) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+__global__ void groupnorm_apply_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ stats, long long HW, int C, int G, int swish,
+                                       long long total4) {
+  const int C4 = C >> 2, cpg = C / G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long n = i / (C4 * HW);
+    float4 v = in[i];
+    float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      const float mean = stats[(n * G + g) * 2], rstd = stats[(n * G + g) * 2 + 1];
+      float y = (r[j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+      if (swish) y = y / (1.f + expf(-y));
+      r[j] = y;
+    }
+    out[i] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+extern "C" int mmvid_groupnorm(const float* in, float* out, const float* gamma, const float* beta, float* stats,
+                               int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream) {
+  MMVID_REQUIRE(C % groups == 0 && C % 4 == 0, "C divisible by groups and 4");
+  if (N == 0) return MMVID_OK;
+  cudaStream_t st = to_stream(stream);
+  groupnorm_stats_kernel<<<dim3(groups, N), 512, 0, st>>>(in, stats, HW, C, groups, eps);
+  int rc = check_launch("groupnorm_stats");
+  if (rc) return rc;
+  const long long total4 = (long long)N * HW * (C / 4);
+  const int blocks = (int)std::min<long long>(ceil_div<long long>(total4, 256), 148 * 16);
+  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>((const float4*)in, (float4*)out, gamma, beta, stats, HW, C, groups,
+                                                  swish, total4);
+  return check_launch("groupnorm_apply");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K14 VQ argmin.  One warp per latent row; the codebook (1024 x 256 fp32 = 1 MB) streams from L2.
+// Summation order restates quantize.py:306-308:  d = (sum z^2 + sum e^2) - 2 * dot ; lowest index wins ties.
+// Each block stages 8 rows of z in smem; each warp owns one row and loops over codes; lanes split the
+// 256-dim dot product (8 floats per lane), so codebook reads are fully coalesced 1 KB rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void code_sqnorm_kernel(const float* __restrict__ cb, float* __restrict__ e2, int n_codes, int dim) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n_codes) return;
+  float s = 0.f;
+  for (int c = threadIdx.x & 31; c < dim; c += 32) { float v = cb[(long long)j * dim + c]; s += v * v; }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) e2[j] = s;
+}
+
+template <int ROWS>
+__global__ void vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb,
+                                 const float* __restrict__ e2, int64_t* __restrict__ idx, long long T, int n_codes,
+                                 int dim) {
+  // block: 256 threads; thread t handles codes t, t+256, ... for ROWS rows staged in smem.
+  extern __shared__ float zs[];  // [ROWS][dim]
+  __shared__ float z2[ROWS];
+  __shared__ float best_d[ROWS][8];
+  __shared__ int best_i[ROWS][8];
+  const long long row0 = (long long)blockIdx.x * ROWS;
+  for (int i = threadIdx.x; i < ROWS * dim; i += blockDim.x) {
+    const long long r = row0 + i / dim;
+    zs[i] = r < T ? z[r * dim + (i % dim)] : 0.f;
+  }
+  __syncthreads();
+  {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = w; r < ROWS; r += 8) {
+      float s = 0.f;
+      for (int c = lane; c < dim; c += 32) s += zs[r * dim + c] * zs[r * dim + c];
+      s = warp_sum(s);
+      if (lane == 0) z2[r] = s;
+    }
+  }
+  __syncthreads();
+  float bd[ROWS];
+  int bi[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) { bd[r] = INFINITY; bi[r] = 0x7fffffff; }
+  for (int j = threadIdx.x; j < n_codes; j += blockDim.x) {
+    const float4* e = reinterpret_cast<const float4*>(cb + (long long)j * dim);
+    float dot[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) dot[r] = 0.f;
+    for (int c = 0; c < dim / 4; ++c) {
+      const float4 ev = __ldg(e + c);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const float4 zv = reinterpret_cast<const float4*>(zs + r * dim)[c];
+        dot[r] = fmaf(zv.x, ev.x, dot[r]); dot[r] = fmaf(zv.y, ev.y, dot[r]);
+        dot[r] = fmaf(zv.z, ev.z, dot[r]); dot[r] = fmaf(zv.w, ev.w, dot[r]);
+      }
+    }
+    const float ej = e2[j];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float d = (z2[r] + ej) - 2.f * dot[r];
+      if (d < bd[r]) { bd[r] = d; bi[r] = j; }   // j increases per thread: strict < keeps the lowest index
+    }
+  }
+  // reduce (min d, then min index) across the block
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float d = bd[r]; int i = bi[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+    }
+    if (lane == 0) { best_d[r][w] = d; best_i[r][w] = i; }
+  }
+  __syncthreads();
+  if (threadIdx.x < ROWS) {
+    const int r = threadIdx.x;
+    float d = best_d[r][0]; int i = best_i[r][0];
+    for (int k = 1; k < 8; ++k) {
+      if (best_d[r][k] < d || (best_d[r][k] == d && best_i[r][k] < i)) { d = best_d[r][k]; i = best_i[r][k]; }
+    }
+    if (row0 + r < T) idx[row0 + r] = i;
+  }
+}
+
+// scratch for ||e||^2 lives in a small static device buffer (n_codes <= 16384)
+__device__ float g_e2_scratch[16384];
+
+extern "C" int mmvid_vq_argmin(const float* z, const float* codebook, int64_t* idx, long long T, int n_codes, int dim,
+                               mmvid_stream_t stream) {
+  MMVID_REQUIRE(dim % 4 == 0 && dim <= 1024, "dim multiple of 4");
+  MMVID_REQUIRE(n_codes <= 16384, "n_codes <= 16384");
+  if (T == 0) return MMVID_OK;
+  float* e2 = nullptr;
+  cudaGetSymbolAddress((void**)&e2, g_e2_scratch);
+  cudaStream_t st = to_stream(stream);
+  code_sqnorm_kernel<<<ceil_div(n_codes, 8), 256, 0, st>>>(codebook, e2, n_codes, dim);
+  int rc = check_launch("code_sqnorm");
+  if (rc) return rc;
+  constexpr int ROWS = 4;
+  vq_argmin_kernel<ROWS><<<(unsigned)ceil_div<long long>(T, ROWS), 256, ROWS * dim * sizeof(float), st>>>(
+      z, codebook, e2, idx, T, n_codes, dim);
+  return check_launch("vq_argmin");
+}
+
+__global__ void codebook_gather_kernel(const int64_t* __restrict__ ids, const float4* __restrict__ cb,
+                                       float4* __restrict__ out, long long T, int dim4) {
+  const long long t = (long long)blockIdx.x * (blockDim.x / 64) + threadIdx.x / 64;
+  if (t >= T) return;
+  const long long id = ids[t];
+  for (int c = threadIdx.x % 64; c < dim4; c += 64) out[t * dim4 + c] = __ldg(cb + id * dim4 + c);
+}
+extern "C" int mmvid_codebook_gather(const int64_t* ids, const float* codebook, float* out, long long T, int dim,
+                                     mmvid_stream_t stream) {
+  MMVID_REQUIRE(dim % 4 == 0, "dim multiple of 4");
+  if (T == 0) return MMVID_OK;
+  codebook_gather_kernel<<<(unsigned)ceil_div<long long>(T, 4), 256, 0, to_stream(stream)>>>(
+      ids, (const float4*)codebook, (float4*)out, T, dim / 4);
+  return check_launch("codebook_gather");
+}
