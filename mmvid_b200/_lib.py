@@ -1,0 +1,91 @@
+"""ctypes binding of libmmvid_b200.so (the C ABI declared in include/mmvid_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmmvid_b200.so")
+
+FP32, TF32, BF16 = 0, 1, 2
+ACT_NONE, ACT_QUICKGELU, ACT_SWISH = 0, 1, 2
+MASK_NONE, MASK_CAUSAL, MASK_PREV = 0, 1, 2
+DT_F32, DT_BF16 = 0, 1
+PRECISIONS = {"fp32": FP32, "tf32": TF32, "bf16": BF16}
+
+_p, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+
+
+class EmbedSegment(C.Structure):
+    _fields_ = [("ids", _p), ("ids_bstride", _ll), ("n", _i), ("seq_off", _i), ("table", _p), ("table2", _p),
+                ("pos", _p), ("pad_value", _ll), ("pad_base", _ll), ("use_pad", _i)]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [("inp", _p), ("w", _p), ("bias", _p), ("residual", _p), ("out", _p)] + \
+               [(n, _i) for n in ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad_t", "pad_l", "Ho", "Wo",
+                                  "upsample", "in_nchw", "out_nchw", "pre_affine", "post_clamp", "precision")]
+
+
+# name -> (restype, argtypes); kept in sync with include/mmvid_b200.h (tests/test_abi.py checks every symbol)
+SIGNATURES = {
+    "mmvid_version": (_i, []),
+    "mmvid_last_error": (C.c_char_p, []),
+    "mmvid_launch_count": (_ll, []),
+    "mmvid_reset_launch_count": (None, []),
+    "mmvid_embed_gather": (_i, [_p, _i, _i, _i, C.POINTER(EmbedSegment), _i, _p]),
+    "mmvid_axial_table": (_i, [_p, _i, _i, _p, _p, _p, C.POINTER(_i), _i, _p]),
+    "mmvid_layernorm": (_i, [_p, _ll, _p, _p, _p, _i, _ll, _i, _f, _p]),
+    "mmvid_linear": (_i, [_p, _i, _ll, _p, _i, _ll, _p, _p, _ll, _p, _i, _ll, _ll, _i, _i, _i, _i, _p]),
+    "mmvid_gemm_batched_f32": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i,
+                                    _f, _p]),
+    "mmvid_softmax_rows": (_i, [_p, _ll, _i, _i, _ll, _i, _p, _i, _p]),
+    "mmvid_attention": (_i, [_p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i, _p]),
+    "mmvid_qkv_split": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mmvid_decode_attention": (_i, [_p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _p]),
+    "mmvid_linear_small_m": (_i, [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p]),
+    "mmvid_kv_append": (_i, [_p, _ll, _p, _p, _i, _i, _i, _i, _p]),
+    "mmvid_vq_argmin": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
+    "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
+    "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),
+    "mmvid_groupnorm": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "mmvid_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "mmvid_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _p]),
+    "mmvid_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _p]),
+    "mmvid_softmax_logits": (_i, [_p, _p, _f, _p, _ll, _i, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"mmvid_b200: CUDA library not found at {LIB_PATH}. Build it with `python -m mmvid_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header drifted apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mmvid_last_error().decode(errors="replace")
+        raise RuntimeError(f"mmvid_b200 {what} failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(load().mmvid_launch_count())
+
+
+def reset_launch_count():
+    load().mmvid_reset_launch_count()

@@ -1,0 +1,67 @@
+"""Multi-GPU sampling: replicas + batch split + ONE all-gather of decoded frames.
+
+The path shards by independent units (each sample of the sampling batch is an independent sequence; the
+reference itself loops over samples serially, dalle_bert.py:618), so there is no data-path collective besides
+the final gather.  One process per GPU (torchrun); backend nccl on GPUs, gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous split of n samples over `world` ranks; the first n % world ranks get one extra."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(t, rank=None, world=None):
+    if t is None:
+        return None
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_bounds(t.shape[0], rank, world)
+    return t[lo:hi]
+
+
+def all_gather_variable(x, sizes=None):
+    """All-gather tensors whose leading dim may differ by rank (ragged batch split).  Pads to the max, gathers
+    with a single collective, then trims.  Returns the concatenation in rank order on every rank."""
+    world = dist.get_world_size()
+    if sizes is None:
+        n = torch.tensor([x.shape[0]], device=x.device, dtype=torch.long)
+        all_n = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(all_n, n)
+        sizes = [int(v) for v in all_n]
+    m = max(sizes)
+    if m == 0:
+        return x
+    pad = torch.zeros((m,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    pad[: x.shape[0]] = x
+    out = torch.empty((world * m,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(out, pad.contiguous())
+    chunks = [out[r * m: r * m + sizes[r]] for r in range(world)]
+    return torch.cat(chunks, 0)
+
+
+@torch.no_grad()
+def generate_images_sharded(model, text, visual=None, **gen_kwargs):
+    """Global batch in, global batch out.  Rank r generates samples [lo_r, hi_r) with its replica and the decoded
+    frames (and token ids) are all-gathered once at the end.  Per-rank RNG: callers seed `seed + rank`
+    (train.py:87 does the same) in throughput mode."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return model.generate_images(text, visual=visual, **gen_kwargs)
+    rank = dist.get_rank()
+    n = text.shape[0]
+    sizes = [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
+    t_loc, v_loc = shard_batch(text, rank, world), shard_batch(visual, rank, world)
+    if t_loc.shape[0] > 0:
+        images, extra, seq = model.generate_images(t_loc, visual=v_loc, **gen_kwargs)
+    else:
+        raise RuntimeError("global batch smaller than world size")
+    images = all_gather_variable(images.contiguous(), sizes)
+    if seq is not None:
+        per = seq.shape[0] // max(t_loc.shape[0], 1)
+        seq = all_gather_variable(seq.contiguous(), [s * per for s in sizes])
+    return images, extra, seq

@@ -1,0 +1,49 @@
+"""CPU: the N>1 sampling path (batch split + single all-gather) on world_size-2 gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _FakeModel:
+    """Stands in for BERT on CPU: deterministic 'frames' derived from the prompt ids (no kernels)."""
+    num_targets, image_seq_len = 2, 4
+
+    def generate_images(self, text, visual=None, **kw):
+        b = text.shape[0]
+        frames = text.float().sum(1).view(b, 1, 1, 1, 1).expand(b, self.num_targets, 3, 4, 4).contiguous()
+        seq = text[:, :1].repeat_interleave(self.num_targets, 0).repeat(1, self.image_seq_len)
+        return frames, [], seq
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmvid_b200.parallel import generate_images_sharded
+    text = torch.arange(n * 5).view(n, 5)
+    images, _, seq = generate_images_sharded(_FakeModel(), text)
+    ref_images, _, ref_seq = _FakeModel().generate_images(text)
+    q.put((rank, bool(torch.equal(images, ref_images)), bool(torch.equal(seq, ref_seq)), tuple(images.shape)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [4, 5])
+def test_sharded_generation_gathers_global_batch(n):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    for rank, ok_i, ok_s, shape in res:
+        assert ok_i and ok_s and shape[0] == n

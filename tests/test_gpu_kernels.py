@@ -1,0 +1,252 @@
+"""GPU parity of each C-ABI kernel against a plain PyTorch fp32 statement of the same op (run with -m gpu).
+
+Tolerances: fp32 CUDA-core path ~1e-5 norm-relative (summation order only); TF32 tensor-core path 1e-3
+(north_star's bar); BF16 path 2e-2 (reported, throughput mode).  Integer outputs must be bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference_math():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from mmvid_b200 import ops
+    return ops
+
+
+def test_library_loads_and_reports_version():
+    from mmvid_b200 import _lib
+    assert _lib.load().mmvid_version() >= 100
+
+
+def test_embed_gather_segments():
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    B, S, D = 3, 11, 64
+    table = torch.randn(40, D, generator=g).cuda()
+    table2 = torch.randn(40, D, generator=g).cuda()
+    pos = torch.randn(6, D, generator=g).cuda()
+    ids = torch.randint(0, 30, (B, 6), generator=g).cuda()
+    ids[:, 4:] = 0  # pads -> unique ids 34+i
+    sp = torch.tensor([[1, 2]]).cuda()
+    out = torch.zeros(B, S, D, device="cuda")
+    ops.embed_gather(out, [dict(ids=sp, seq_off=0, table=table, table2=table2),
+                           dict(ids=ids, seq_off=2, table=table, pos=pos, pad=(0, 34)),
+                           dict(ids=ids[:, :3].contiguous(), seq_off=8, table=table2)])
+    rid = torch.where(ids == 0, torch.arange(6, device="cuda") + 34, ids)
+    ref = torch.cat([(table[sp] + table2[sp]).expand(B, 2, D), table[rid] + pos, table2[ids[:, :3]]], 1)
+    assert torch.equal(out, ref)
+
+
+def test_axial_table_matches_broadcast_sum():
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    D = 32
+    w = [torch.randn(1, 3, 1, 1, D, generator=g).cuda(), torch.randn(1, 1, 4, 1, D, generator=g).cuda(),
+         torch.randn(1, 1, 1, 5, D, generator=g).cuda()]
+    t = ops.axial_table(w, (3, 4, 5))
+    ref = ((w[0] + w[1]) + w[2]).reshape(60, D)
+    assert torch.equal(t, ref)
+
+
+@pytest.mark.parametrize("rows,D", [(5, 128), (1000, 768), (33, 1024)])
+def test_layernorm(rows, D):
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(rows, D, generator=g) * 3 + 1).cuda()
+    w, b = torch.randn(D, generator=g).cuda(), torch.randn(D, generator=g).cuda()
+    ref = F.layer_norm(x, (D,), w, b, 1e-5)
+    assert relerr(ops.layernorm(x, w, b), ref) < 2e-6
+    assert relerr(ops.layernorm(x, w, b, out_dtype=torch.bfloat16).float(), ref) < 5e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (130, 192, 128), (2115, 2304, 768), (565, 768, 3072), (300, 1024, 768)])
+def test_linear_bias_act_residual(prec, M, N, K):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    ref0 = F.linear(a.double(), w.double(), bias.double())
+    ref = (ref0 * torch.sigmoid(1.702 * ref0) + res.double()).float()
+    if prec == "bf16":
+        out = ops.linear(a.bfloat16(), w.bfloat16(), bias, act=ops.ACT_QUICKGELU, residual=res, precision=prec)
+    else:
+        out = ops.linear(a, w, bias, act=ops.ACT_QUICKGELU, residual=res, precision=prec)
+    e = relerr(out, ref)
+    assert e < TOL[prec], f"{prec} {M}x{N}x{K}: {e}"
+    # plain (no epilogue) + in-place residual aliasing
+    ref2 = (F.linear(a.double(), w.double()) + res.double()).float()
+    buf = res.clone()
+    if prec == "bf16":
+        ops.linear(a.bfloat16(), w.bfloat16(), None, residual=buf, precision=prec, out=buf)
+    else:
+        ops.linear(a, w, None, residual=buf, precision=prec, out=buf)
+    assert relerr(buf, ref2) < TOL[prec]
+
+
+def test_linear_bf16_output_and_unaligned_n():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(200, 256, generator=g).cuda()
+    w = (torch.randn(130, 256, generator=g) / 16).cuda()  # N not a multiple of the tile or of 4-aligned vectors? (130 % 4 = 2)
+    ref = F.linear(a, w)
+    out = ops.linear(a, w, precision="tf32")
+    assert relerr(out, ref) < 1e-3
+    o16 = ops.linear(a.bfloat16(), w[:128].bfloat16().contiguous(), precision="bf16", out_dtype=torch.bfloat16)
+    assert o16.dtype == torch.bfloat16 and relerr(o16.float(), ref[:, :128]) < 2e-2
+
+
+def _attn_ref(qkv, B, S, H, mask):
+    D = H * 64
+    q, k, v = qkv.view(B, S, 3, H, 64).double().unbind(2)
+    q, k, v = [t.transpose(1, 2) for t in (q, k, v)]
+    att = q @ k.transpose(-1, -2) / 8.0
+    if mask is not None:
+        att = att + mask.double().to(att.device)
+    o = torch.softmax(att, -1) @ v
+    return o.transpose(1, 2).reshape(B * S, D).float()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("B,S,H,kind", [(2, 37, 2, "prev"), (1, 200, 3, "causal"), (1, 565, 12, "prev"), (2, 128, 2, "none"),
+                                        (1, 300, 2, "causal")])
+def test_attention_masks(prec, B, S, H, kind):
+    ops = _ops()
+    from oracle import mmvid_oracle as O
+    g = torch.Generator().manual_seed(S + H)
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g).cuda()
+    rows = (S // 3, S // 3 + 1)
+    if kind == "prev":
+        mask, mk, pr = O.build_attention_mask(S, "mask_prev", rows), ops.MASK_PREV, rows
+    elif kind == "causal":
+        mask, mk, pr = O.build_attention_mask(S, "causal"), ops.MASK_CAUSAL, ()
+    else:
+        mask, mk, pr = None, ops.MASK_NONE, ()
+    ref = _attn_ref(qkv, B, S, H, mask)
+    if prec == "fp32":
+        out = ops.attention_fp32(qkv, B, S, H, mk, torch.tensor(list(pr) or [0], dtype=torch.int32, device="cuda"))
+    else:
+        out = ops.attention_tc(qkv, B, S, H, mk, pr, prec,
+                               out_dtype=torch.bfloat16 if prec == "bf16" else torch.float32).float()
+    e = relerr(out, ref)
+    assert e < TOL[prec], f"{prec} {kind} S={S}: {e}"
+
+
+def test_vq_argmin_bit_exact_and_ties():
+    ops = _ops()
+    from oracle import mmvid_oracle as O
+    g = torch.Generator().manual_seed(7)
+    cb = (torch.randn(1024, 256, generator=g) * 0.3)
+    z = torch.randn(777, 256, generator=g) * 0.2
+    ref = torch.argmin(O.vq_distances(z, cb), dim=1)
+    idx = ops.vq_argmin(z.cuda(), cb.cuda())
+    assert idx.dtype == torch.int64 and torch.equal(idx.cpu(), ref)
+    # exact ties: duplicated codewords -> lowest index must win (torch.argmin semantics)
+    cb2 = cb.clone()
+    cb2[900] = cb2[17]
+    cb2[400] = cb2[17]
+    z2 = cb2[[17, 400, 900, 5]] + 1e-4
+    assert ops.vq_argmin(z2.cuda(), cb2.cuda()).cpu().tolist() == [17, 17, 17, 5]
+    # empty input
+    assert ops.vq_argmin(torch.empty(0, 256).cuda(), cb.cuda()).numel() == 0
+
+
+def test_codebook_gather():
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    cb = torch.randn(1024, 256, generator=g).cuda()
+    ids = torch.randint(0, 1024, (3, 16), generator=g).cuda()
+    assert torch.equal(ops.codebook_gather(ids, cb).view(3, 16, 256), cb[ids])
+
+
+@pytest.mark.parametrize("C,HW", [(128, 64), (512, 16), (256, 1024)])
+def test_groupnorm_swish(C, HW):
+    ops = _ops()
+    g = torch.Generator().manual_seed(C)
+    N, H = 3, int(math.sqrt(HW))
+    x = (torch.randn(N, C, H, H, generator=g) * 2 + 0.5).cuda()
+    w, b = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+    ref = F.group_norm(x, 32, w, b, 1e-6)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    assert relerr(ops.groupnorm(x_nhwc, w, b).permute(0, 3, 1, 2), ref) < 5e-6
+    assert relerr(ops.groupnorm(x_nhwc, w, b, swish=True).permute(0, 3, 1, 2), ref * torch.sigmoid(ref)) < 5e-6
+
+
+def _pack(w):
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+def test_conv_variants_match_torch():
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    N, Cin, Cout, H = 2, 128, 256, 16
+    x = torch.randn(N, Cin, H, H, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    res = torch.randn(N, H, H, Cout, generator=g).cuda()
+    # 3x3 stride 1 pad 1 (+ residual)
+    ref = F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+    assert relerr(ops.conv2d(xn, _pack(w), b), ref) < 1e-5
+    assert relerr(ops.conv2d(xn, _pack(w), b, residual=res), ref + res) < 1e-5
+    # Downsample: pad (0,1,0,1) then 3x3 stride 2 (model.py:77-81)
+    ref = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2).permute(0, 2, 3, 1)
+    assert relerr(ops.conv2d(xn, _pack(w), b, stride=2, pad=(0, 0), out_hw=(H // 2, H // 2)), ref) < 1e-5
+    # Upsample: nearest x2 then 3x3 (model.py:56-62)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1).permute(0, 2, 3, 1)
+    assert relerr(ops.conv2d(xn, _pack(w), b, upsample=True), ref) < 1e-5
+    # first layer: NCHW input in [0,1] with fused 2x-1; last layer: NCHW output with fused clamp/rescale
+    img = torch.rand(N, 3, 32, 32, generator=g).cuda()
+    w3 = (torch.randn(128, 3, 3, 3, generator=g) / 5).cuda()
+    b3 = torch.randn(128, generator=g).cuda()
+    ref = F.conv2d(2 * img - 1, w3, b3, padding=1).permute(0, 2, 3, 1)
+    assert relerr(ops.conv2d(img, _pack(w3), b3, in_nchw=True, pre_affine=True), ref) < 1e-5
+    wl = (torch.randn(3, Cin, 3, 3, generator=g) / 10).cuda()
+    bl = torch.randn(3, generator=g).cuda()
+    ref = (F.conv2d(x, wl, bl, padding=1).clamp(-1, 1) + 1) * 0.5
+    assert relerr(ops.conv2d(xn, _pack(wl), bl, out_nchw=True, post_clamp=True), ref) < 1e-5
+
+
+def test_softmax_logits_and_noise():
+    ops = _ops()
+    g = torch.Generator().manual_seed(10)
+    l = torch.randn(70, 1024, generator=g).cuda()
+    nz = torch.randn(70, 1024, generator=g).cuda()
+    assert relerr(ops.softmax_logits(l), torch.softmax(l, -1)) < 1e-6
+    assert relerr(ops.softmax_logits(l, nz, 0.7), torch.softmax(l + 0.7 * nz, -1)) < 1e-6
+
+
+def test_decode_kernels_match_full_attention():
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    B, H, S_max, L = 3, 4, 50, 37
+    D = H * 64
+    qkv_all = torch.randn(B, L, 3 * D, generator=g).cuda()
+    kc = torch.zeros(B, H, S_max, 64, device="cuda")
+    vc = torch.zeros(B, H, S_max, 64, device="cuda")
+    for t in range(L):
+        ops.kv_append(qkv_all[:, t].contiguous(), kc, vc, t)
+    out = ops.decode_attention(qkv_all[:, L - 1].contiguous(), kc, vc, L)
+    ref = _attn_ref(qkv_all.reshape(B * L, 3 * D), B, L, H, torch.full((L, L), float("-inf")).triu_(1))
+    assert relerr(out, ref.view(B, L, D)[:, -1]) < 1e-5
+    a = torch.randn(B, 256, generator=g).cuda()
+    w = torch.randn(100, 256, generator=g).cuda() / 16
+    bias = torch.randn(100, generator=g).cuda()
+    res = torch.randn(B, 100, generator=g).cuda()
+    assert relerr(ops.linear_small_m(a, w, bias, residual=res), F.linear(a, w, bias) + res) < 1e-5

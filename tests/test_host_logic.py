@@ -1,0 +1,100 @@
+"""CPU: host-side logic of the drop-in classes (no kernels launched): shapes, state-dict keys, schedules,
+visual-control erasing, batch sharding arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from cases import BERT_CASES
+from helpers import build_artv, build_bert
+from oracle import mmvid_oracle as O
+
+
+def test_bert_sequence_bookkeeping_matches_reference_formulas():
+    cfg = dict(BERT_CASES["bert_tiny"])
+    m, _ = build_bert(cfg, device="cpu")
+    n = (cfg["image_size"] // 16) ** 2
+    assert m.image_seq_len == n and m.target_seq_len == cfg["num_targets"] * n
+    assert m.total_seq_len == 1 + cfg["text_seq_len"] + cfg["num_visuals"] * n + 2 + cfg["num_targets"] * n
+    assert m.st1_tok_index == 1 + cfg["text_seq_len"] + cfg["num_visuals"] * n and m.vid_tok_index == m.st1_tok_index + 1
+    assert m.transformer.mask_rows == (m.st1_tok_index, m.vid_tok_index)
+    assert m.image_token_lut == {"[MASK]": 1024, "[SEP]": 1025}
+    assert m.text_emb.weight.shape[0] == cfg["vocab"] + cfg["text_seq_len"]
+    assert all(not p.requires_grad for p in m.vae.parameters())
+
+
+def test_shape_A_and_B_sequence_lengths():
+    # SURVEY.md appendix B shape calculator
+    for L, px, V, want in ((64, 256, 0, 2115), (64, 256, 1, 2371), (50, 128, 0, 565), (50, 128, 1, 629)):
+        s = O.BertSpec(dim=768, text_seq_len=L, num_text_tokens=49408, num_visuals=V, num_targets=8, image_size=px)
+        assert s.total_seq_len == want
+    a = O.ArtvSpec(dim=768, text_seq_len=64, num_text_tokens=49408, num_visuals=1, num_targets=8, image_size=256)
+    assert (a.total_seq_len, a.total_tokens, a.num_control_tokens) == (2368, 51776, 50752)
+
+
+def test_mask_predict_schedules_match_oracle():
+    from mmvid_b200.dalle_bert import DEFAULT_MP_CONFIG, mask_predict_schedules
+    for N in (8, 512, 2048, 1792):
+        assert mask_predict_schedules(N, DEFAULT_MP_CONFIG) == tuple(O.mask_predict_schedules(N, O.DEFAULT_MP_CONFIG)) or \
+            list(mask_predict_schedules(N, DEFAULT_MP_CONFIG)) == list(O.mask_predict_schedules(N, O.DEFAULT_MP_CONFIG))
+    n, temp = mask_predict_schedules(2048, DEFAULT_MP_CONFIG)
+    assert len(n) == 50 and len(temp) == 50 and n[0] == int(2048 * 0.9) and n[10] == 256 and n[20] == 128
+
+
+def _face_reference(grid, vc_mode, face_mode, MASK):
+    # independent statement of dalle_bert.py:796-848 on a [b,t,8,8] grid
+    out = torch.full_like(grid, MASK)
+    if vc_mode == "face_8x8":
+        if face_mode == "eyes_nose":
+            out[:, :, 2:5, 1:7] = grid[:, :, 2:5, 1:7]
+        else:
+            out[:, :, 5:7, 2:6] = grid[:, :, 5:7, 2:6]
+    elif vc_mode == "face2_8x8":
+        out[:, 0] = grid[:, 0]
+        out[:, 1:, 2:6, 2:6] = grid[:, 1:, 2:6, 2:6]
+    elif vc_mode == "face3_8x8":
+        out[:, 0] = grid[:, 0]
+        out[:, :, 2:6, 2:6] = grid[:, :, 2:6, 2:6]
+    elif vc_mode == "mask_8x8":
+        out[:, :, 1:7, 1:7] = grid[:, :, 1:7, 1:7]
+    return out
+
+
+@pytest.mark.parametrize("vc_mode,face_mode", [("face_8x8", "eyes_nose"), ("face_8x8", "mouth"), ("face2_8x8", "x"),
+                                               ("face3_8x8", "x"), ("mask_8x8", "x")])
+def test_erase_codebook_face_windows(vc_mode, face_mode):
+    cfg = dict(BERT_CASES["bert_tiny"], image_size=128, num_visuals=2)
+    m, _ = build_bert(cfg, device="cpu")
+    ids = torch.randint(0, 1024, (3, 2 * 64))
+    got = m.erase_codebook_face(ids.clone(), vc_mode, face_mode).view(3, 2, 8, 8)
+    assert torch.equal(got, _face_reference(ids.view(3, 2, 8, 8), vc_mode, face_mode, 1024))
+
+
+def test_random_erase_half_and_artv_pad_ids():
+    cfg = dict(BERT_CASES["bert_tiny"], image_size=128)
+    m, _ = build_bert(cfg, device="cpu")
+    ids = torch.randint(0, 1024, (2, 64))
+    out = m.random_erase_codebook(ids.clone(), None, erase_half=True).view(2, 1, 8, 8)
+    assert (out[:, :, 4:] == 1024).all() and torch.equal(out[:, :, :4], ids.view(2, 1, 8, 8)[:, :, :4])
+    from cases import ARTV_CASES
+    a, _ = build_artv(ARTV_CASES["artv_tiny"], device="cpu")
+    assert a._allowed_range(0) == (0, a.num_text_tokens)
+    assert a._allowed_range(a.text_seq_len) == (a.num_text_tokens, a.num_control_tokens)
+    assert a._allowed_range(a.control_seq_len) == (a.num_control_tokens, a.total_tokens)
+
+
+def test_training_forward_is_an_explicit_not_implemented():
+    m, _ = build_bert(BERT_CASES["bert_tiny_nov"], device="cpu")
+    # no silent wrong answer: the forward kernels need CUDA, the training losses are not built yet
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        m(torch.zeros(2, 5, dtype=torch.long), target=torch.zeros(2, 3, 3, 32, 32), return_loss=True)
+
+
+def test_shard_bounds_cover_batch_exactly():
+    from mmvid_b200.parallel import shard_bounds
+    for n in (1, 7, 8, 32, 33):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
