@@ -130,9 +130,3 @@ extern "C" int mmvid_decode_attention(const float* q, long long q_bstride, const
   return check_launch("decode_attention");
 }
 
-// tensor-core conv: implemented in tc_conv.cu once available; until then the fp32 implicit GEMM is the only path
-extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) __attribute__((weak));
-extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
-  (void)p; (void)st;
-  return fail(MMVID_EUNSUPPORTED, "tensor-core conv2d not built%s");
-}

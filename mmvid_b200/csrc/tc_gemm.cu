@@ -70,6 +70,8 @@ struct EpiArgs {
   int c_bf16;
   long long M;
   int N, K, act;
+  // implicit-GEMM conv (CONV=true): 128-pixel M tile = box {BW, BH, BNI} of the NHWC input, K = (tap, channel block)
+  int cCin, cKW, cPadT, cPadL, cBW, cBH, cBNI, cW, cH;
 };
 
 template <int BN>
@@ -77,7 +79,7 @@ constexpr size_t gemm_smem_bytes() {
   return (size_t)STAGES * (BM * 128 + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-template <bool TF32, int BN>
+template <bool TF32, int BN, bool CONV>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, EpiArgs e) {
   extern __shared__ uint8_t smem_raw[];
@@ -93,6 +95,16 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int num_k = (e.K + BKE - 1) / BKE;
+  // conv: decompose the tile's first pixel into (image, row, col); tiles never straddle rows partially because
+  // BW = min(W,128), BH = min(H, 128/BW), BNI = 128/(BW*BH) and W, H are powers of two
+  int cx0 = 0, cy0 = 0, cn0 = 0, cblocks = 1;
+  if constexpr (CONV) {
+    const long long pix = (long long)m0;
+    cx0 = (int)(pix % e.cW);
+    cy0 = (int)((pix / e.cW) % e.cH);
+    cn0 = (int)(pix / ((long long)e.cW * e.cH));
+    cblocks = e.cCin / BKE;
+  }
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -118,7 +130,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* a = tiles + s * STAGE_BYTES;
-        tma_load_2d(a, &tmA, &full[s], kb * BKE, m0);
+        if constexpr (CONV) {
+          const int tap = kb / cblocks, cb = kb - tap * cblocks;
+          const int ky = tap / e.cKW, kx = tap - ky * e.cKW;
+          // halo taps use negative / past-the-edge coordinates: TMA zero-fills, which IS the conv zero padding
+          tma_load_4d(a, &tmA, &full[s], cb * BKE, cx0 + kx - e.cPadL, cy0 + ky - e.cPadT, cn0);
+        } else {
+          tma_load_2d(a, &tmA, &full[s], kb * BKE, m0);
+        }
         tma_load_2d(a + A_BYTES, &tmB, &full[s], kb * BKE, n0);
       }
     }
@@ -218,17 +237,17 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
   }
 }
 
-template <bool TF32, int BN>
+template <bool TF32, int BN, bool CONV = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs& e, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = gemm_smem_bytes<BN>();
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(err));
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div<long long>(e.M, BM), (unsigned)ceil_div(e.N, BN));
-  gemm_tc_kernel<TF32, BN><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, e);
+  gemm_tc_kernel<TF32, BN, CONV><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, e);
   return check_launch("gemm_tc");
 }
 
@@ -264,7 +283,49 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
     int rc = make_tensor_map(&tmB, W, w_dtype, 2, dims, str, box);
     if (rc) return rc;
   }
-  EpiArgs e{bias, residual, ldr, C, ldc, c_dtype == MMVID_DT_BF16, M, N, K, act};
+  EpiArgs e{bias, residual, ldr, C, ldc, c_dtype == MMVID_DT_BF16, M, N, K, act, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (tf32) return BN == 64 ? launch<true, 64>(tmA, tmB, e, st) : launch<true, 128>(tmA, tmB, e, st);
   return BN == 64 ? launch<false, 64>(tmA, tmB, e, st) : launch<false, 128>(tmA, tmB, e, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core conv2d (stride 1, NHWC fp32, kind::tf32): implicit GEMM whose A tiles are fetched by 4-D TMA
+// boxes {32 channels, BW, BH, BNI} at tap-shifted coordinates; out-of-range halo elements are zero-filled by
+// the TMA unit, so neither an im2col buffer nor a padded copy of the activation ever exists.
+// Requirements: stride 1, Cin % 32 == 0, Cout % 4 == 0, H and W powers of two, NHWC in/out.
+// Everything else (first 3-channel conv, stride-2 downsample, 3-channel output conv) stays on the fp32 path.
+// ------------------------------------------------------------------------------------------------
+extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  MMVID_REQUIRE(p->precision == MMVID_TF32, "tensor-core conv runs kind::tf32");
+  MMVID_REQUIRE(p->stride == 1 && !p->in_nchw && !p->out_nchw && !p->pre_affine && !p->post_clamp && !p->upsample,
+                "tc conv: stride 1, NHWC, no fused resampling");
+  MMVID_REQUIRE(p->Cin % 32 == 0 && p->Cout % 4 == 0, "tc conv: Cin % 32 == 0, Cout % 4 == 0");
+  MMVID_REQUIRE(pow2(p->H) && pow2(p->W) && p->Ho == p->H && p->Wo == p->W, "tc conv: power-of-two 'same' convolution");
+  const int BW = p->W < 128 ? p->W : 128;
+  const int BH = (128 / BW) < p->H ? (128 / BW) : p->H;
+  const int BNI = 128 / (BW * BH);
+  const long long M = (long long)p->N * p->H * p->W;
+  const int K = p->KH * p->KW * p->Cin;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+    uint64_t str[3] = {(uint64_t)p->Cin * 4, (uint64_t)p->W * p->Cin * 4, (uint64_t)p->H * p->W * p->Cin * 4};
+    uint32_t box[4] = {32, (uint32_t)BW, (uint32_t)BH, (uint32_t)BNI};
+    int rc = make_tensor_map(&tmA, p->in, MMVID_DT_F32, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  const long long tiles128 = ceil_div<long long>(M, BM) * ceil_div(p->Cout, 128);
+  const int BN = (tiles128 < 200) ? 64 : 128;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)p->Cout};
+    uint64_t str[1] = {(uint64_t)K * 4};
+    uint32_t box[2] = {32, (uint32_t)BN};
+    int rc = make_tensor_map(&tmB, p->w, MMVID_DT_F32, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  EpiArgs e{p->bias, p->residual, (long long)p->Cout, p->out, (long long)p->Cout, 0, M, p->Cout, K, MMVID_ACT_NONE,
+            p->Cin, p->KW, p->pad_t, p->pad_l, BW, BH, BNI, p->W, p->H};
+  return BN == 64 ? launch<true, 64, true>(tmA, tmB, e, st) : launch<true, 128, true>(tmA, tmB, e, st);
 }

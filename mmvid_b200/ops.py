@@ -288,3 +288,12 @@ def conv2d(x, w_packed, bias, *, stride=1, pad=(1, 1), out_hw=None, upsample=Fal
     p.pre_affine, p.post_clamp, p.precision = int(pre_affine), int(post_clamp), precision_id(precision)
     L.check(lib.mmvid_conv2d(C.byref(p), _stream()), "conv2d")
     return out
+
+
+def upsample2x(x):
+    """nearest x2 on NHWC float32 (model.py:57-59)."""
+    lib = L.load()
+    N, H, W, Cc = x.shape
+    out = torch.empty(N, 2 * H, 2 * W, Cc, device=x.device, dtype=torch.float32)
+    L.check(lib.mmvid_upsample2x(_ptr(x), _ptr(out), N, H, W, Cc, _stream()), "upsample2x")
+    return out

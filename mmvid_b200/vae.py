@@ -190,7 +190,17 @@ class VQGanVAE1024(nn.Module):
         return PRECISIONS[self.precision] if isinstance(self.precision, str) else self.precision
 
     def _conv3(self, x, conv, **kw):
-        return ops.conv2d(x, self._pack.conv(conv.weight), conv.bias, precision=FP32, **kw)
+        """3x3 conv.  precision 'tf32': stride-1 NHWC convs with Cin % 32 == 0 run on tcgen05 through 4-D TMA
+        tiles (nearest-x2 upsampling is materialised first); the 3-channel input/output convs and the stride-2
+        downsample stay on the fp32 implicit-GEMM path."""
+        w = self._pack.conv(conv.weight)
+        tc_ok = (self._prec() != FP32 and kw.get("stride", 1) == 1 and not kw.get("in_nchw") and not kw.get("out_nchw")
+                 and w.shape[3] % 32 == 0 and w.shape[0] % 4 == 0)
+        if tc_ok:
+            if kw.pop("upsample", False):
+                x = ops.upsample2x(x)
+            return ops.conv2d(x, w, conv.bias, precision=TF32, **kw)
+        return ops.conv2d(x, w, conv.bias, precision=FP32, **kw)
 
     def _conv1(self, x, conv, residual=None):
         N, H, W, C = x.shape

@@ -10,10 +10,11 @@ run() { # name, timeout, args...
   tail -n 3 gpurun_out/$name.log | tee -a gpurun_out/summary.txt
 }
 rm -f gpurun_out/summary.txt
-run k_fp32 900 tests/test_gpu_kernels.py -k "not tf32 and not bf16"
+run k_fp32 900 tests/test_gpu_kernels.py -k "not tf32 and not bf16 and not tensor_core"
 run k_lin_tf32 300 tests/test_gpu_kernels.py -k "linear and tf32"
+run k_conv_tf32 300 tests/test_gpu_kernels.py -k "conv3x3_tensor_core"
 run k_lin_bf16 300 tests/test_gpu_kernels.py -k "linear and bf16 or bf16_output"
 run k_att_tf32 300 tests/test_gpu_kernels.py -k "attention and tf32"
 run k_att_bf16 300 tests/test_gpu_kernels.py -k "attention and bf16"
-run m_fp32 1500 tests/test_gpu_models.py -k "fp32 or vae or generate or kv_cache"
-run m_tc 1200 tests/test_gpu_models.py -k "tf32 or bf16 or batched"
+run m_fp32 1500 tests/test_gpu_models.py -k "(fp32 or vae or generate or kv_cache) and not tensor_core"
+run m_tc 1200 tests/test_gpu_models.py -k "tf32 or bf16 or batched or tensor_core"

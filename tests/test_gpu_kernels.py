@@ -223,6 +223,32 @@ def test_conv_variants_match_torch():
     assert relerr(ops.conv2d(xn, _pack(wl), bl, out_nchw=True, post_clamp=True), ref) < 1e-5
 
 
+@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 128, 128, 32), (3, 512, 512, 4), (1, 256, 128, 128), (5, 256, 512, 8),
+                                          (2, 128, 256, 16)])
+def test_conv3x3_tensor_core_tf32(N, Cin, Cout, H):
+    """tcgen05 implicit-GEMM conv: 4-D TMA tiles with halo zero-fill vs F.conv2d (fp64 reference)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 1000 + Cin + H)
+    x = torch.randn(N, Cin, H, H, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, H, H, Cout, generator=g).cuda()
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    out = ops.conv2d(xn, _pack(w), b, precision="tf32")
+    e = relerr(out, ref)
+    assert e < 1e-3, e
+    out = ops.conv2d(xn, _pack(w), b, residual=res, precision="tf32")
+    assert relerr(out, ref + res) < 1e-3
+
+
+def test_upsample2x():
+    ops = _ops()
+    x = torch.randn(2, 5, 7, 8).cuda()
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(ops.upsample2x(x), ref)
+
+
 def test_softmax_logits_and_noise():
     ops = _ops()
     g = torch.Generator().manual_seed(10)

@@ -66,6 +66,18 @@ def test_vae_indices_bit_exact_and_pixels(name):
     assert float(dec.min()) >= 0.0 and float(dec.max()) <= 1.0
 
 
+@pytest.mark.parametrize("name", ["vae_64", "vae_128"])
+def test_vae_decode_tf32_tensor_core_pixels(name):
+    """Decoder on tcgen05 (kind::tf32 convs + 1x1 GEMMs): pixels within 1e-3 of the reference's fp32 output."""
+    cfg = VAE_CASES[name]
+    fx = load_fixture(name)
+    vae, _ = build_vae(cfg["image_size"], cfg["seed"], precision="tf32")
+    dec = vae.decode(fx["indices"].cuda())
+    e = relerr(dec, fx["decoded"])
+    print(f"{name}: tf32 decode relerr {e:.2e}")
+    assert e < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ BERT
 _BERT_CACHE = {}
 
