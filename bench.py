@@ -45,7 +45,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=4, help="prompts per GPU per step")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"])
     ap.add_argument("--mp-steps", type=int, default=20)
+    ap.add_argument("--vae-precision", default=None, choices=["tf32", "fp32"],
+                    help="VQGAN conv precision (default: tf32 tensor cores unless --precision fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="ncu mode: no warm-up, one step, no side measurements")
     return ap.parse_args()
 
 
@@ -145,6 +148,7 @@ def workload_config(args, per_gpu_batch):
             "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "seq_len": S,
             "parallelism": f"replicas x{args.gpus}, batch split, one all-gather of frames",
             "precision": args.precision,
+            "vae_precision": args.vae_precision or ("fp32" if args.precision == "fp32" else "tf32"),
             "l2": "explicit 256 MiB L2 flush between timed steps (outside the timed events)"}
 
 
@@ -192,7 +196,8 @@ def build_model(args, device):
     from mmvid_b200.vae import VQGanVAE1024
     cfg = SHAPES[args.shape]
     torch.manual_seed(1234)
-    vae = VQGanVAE1024(vae_path=None, image_size=cfg["image_size"])
+    vprec = args.vae_precision or ("fp32" if args.precision == "fp32" else "tf32")
+    vae = VQGanVAE1024(vae_path=None, image_size=cfg["image_size"], precision=vprec)
     vae.image_size = cfg["image_size"]
     # default VQ init U(+-1/1024) is degenerate for decoding; use unit-scale codes (random-init weights, no checkpoint)
     vae.model.quantize.embedding.weight.data.normal_(0, 0.3)
@@ -319,6 +324,12 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t) / 1000.0  # seconds, max over ranks
 
+    if args.profile:
+        step(False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(max(args.warmup, 3)):
         step(False)
     torch.cuda.synchronize()
