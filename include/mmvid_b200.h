@@ -148,9 +148,21 @@ typedef struct {
 int mmvid_conv2d(const mmvid_conv_params* p, mmvid_stream_t stream);
 
 /* K11 GroupNorm(32 groups, eps) + optional swish on NHWC (model.py:38-42, 33-35):
- *   stats scratch: float [N*32*2].  out may alias in. */
+ *   stats scratch: mmvid_groupnorm_scratch_floats(N, groups) floats.  out may alias in. */
 int mmvid_groupnorm(const float* in, float* out, const float* gamma, const float* beta, float* stats_scratch,
                     int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream);
+
+/* size (in floats) of the stats scratch mmvid_groupnorm / mmvid_conv_out_fused need for N images */
+long long mmvid_groupnorm_scratch_floats(int N, int groups);
+/* statistics only: stats[n, g] = (mean, rstd) at the start of the scratch buffer */
+int mmvid_groupnorm_stats(const float* in, float* stats_scratch, int N, int HW, int C, int groups, float eps,
+                          mmvid_stream_t stream);
+
+/* Decoder tail fused (model.py:578-581 + vae.py:55): GroupNorm + swish + 3x3 conv to Cout <= 4 channels
+ * (+ clamp(-1,1)*0.5+0.5), NHWC in, NCHW out.  w packed [Cout,3,3,C]. */
+int mmvid_conv_out_fused(const float* in, const float* gamma, const float* beta, const float* w, const float* bias,
+                         float* out, float* stats_scratch, int N, int H, int W, int C, int Cout, int groups, float eps,
+                         int post_clamp, mmvid_stream_t stream);
 
 /* nearest x2 upsample NHWC (used only when not fused into the conv) */
 int mmvid_upsample2x(const float* in, float* out, int N, int H, int W, int C, mmvid_stream_t stream);

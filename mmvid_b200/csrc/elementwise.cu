@@ -314,31 +314,86 @@ extern "C" int mmvid_upsample2x(const float* in, float* out, int N, int H, int W
 }
 
 // ------------------------------------------------------------------------------------------------
-// K11 GroupNorm(+swish) on NHWC.  Pass 1: per-(n, group) mean / rstd (one block each, two-pass over
-// the group's HW x (C/G) elements, float accumulation of centered squares).  Pass 2: elementwise apply.
+// K11 GroupNorm(+swish) on NHWC.
+// Pass 1 (one HBM read, fully coalesced): each block owns a contiguous slab of pixels of one image and walks
+// it row by row ([pixels, C] is contiguous), every thread accumulating SHIFTED first/second moments of its
+// own 4 channels: s1 = sum(x-K), s2 = sum((x-K)^2) with K = that channel's value at pixel 0 of the image
+// (keeps the cancellation in var = E[(x-K)^2] - E[x-K]^2 mild).  Threads -> groups through shared memory;
+// per-(image, slab, group) partials go to scratch and are combined in a FIXED order by the finalize kernel,
+// so the statistics are deterministic (no atomics) - bit-exact VQ ids need run-to-run reproducibility.
+// Pass 2: elementwise normalise * gamma + beta (+ swish).
 // ------------------------------------------------------------------------------------------------
-__global__ void groupnorm_stats_kernel(const float* __restrict__ in, float* __restrict__ stats, int HW, int C,
-                                       int G, float eps) {
-  __shared__ float red[32];
-  const int g = blockIdx.x, n = blockIdx.y;
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_SLABS = 64;
+
+__global__ void __launch_bounds__(GN_THREADS) groupnorm_partial_kernel(const float* __restrict__ in,
+                                                                      float* __restrict__ partial, int HW, int C, int G,
+                                                                      int slabs) {
+  extern __shared__ float sm[];  // [2][C]
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int C4 = C >> 2;
+  const int lanes_per_row = C4;                       // threads needed to cover one pixel row
+  const int rows_per_iter = GN_THREADS / lanes_per_row;  // C <= 1024 -> >= 1
+  const int c4 = threadIdx.x % lanes_per_row, rsub = threadIdx.x / lanes_per_row;
+  const long long img = (long long)n * HW * C;
+  const int p_per_slab = (HW + slabs - 1) / slabs;
+  const int p0 = slab * p_per_slab, p1 = min(HW, p0 + p_per_slab);
+  const float4 K = *reinterpret_cast<const float4*>(in + img + c4 * 4);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rsub < rows_per_iter) {
+    for (int p = p0 + rsub; p < p1; p += rows_per_iter) {
+      const float4 v = *reinterpret_cast<const float4*>(in + img + (long long)p * C + c4 * 4);
+      float d;
+      d = v.x - K.x; s1[0] += d; s2[0] = fmaf(d, d, s2[0]);
+      d = v.y - K.y; s1[1] += d; s2[1] = fmaf(d, d, s2[1]);
+      d = v.z - K.z; s1[2] += d; s2[2] = fmaf(d, d, s2[2]);
+      d = v.w - K.w; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
+    }
+  }
+  // reduce the row sub-lanes per channel, in a fixed order
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+  __syncthreads();
+  for (int r = 0; r < rows_per_iter; ++r) {
+    if (rsub == r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sm[c4 * 4 + j] += s1[j]; sm[C + c4 * 4 + j] += s2[j]; }
+    }
+    __syncthreads();
+  }
+  // per group: combine channels.  With shift K_c per channel: sum(x) = s1_c + cnt*K_c ; sum over the group of
+  // centered moments is finished in the finalize kernel from (cnt, sum x, sum (x-K_c)^2, K_c) -> we emit, per channel
+  // quad, moments re-expressed about the GROUP shift Kg = K of the group's first channel.
   const int cpg = C / G;
-  const float* base = in + (long long)n * HW * C + g * cpg;
-  const long long cnt = (long long)HW * cpg;
-  float s = 0.f;
-  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const long long p = i / cpg; const int c = (int)(i % cpg);
-    s += base[p * C + c];
+  const float cnt = (float)(p1 - p0);
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    const float Kg = in[img + g * cpg];
+    float a1 = 0.f, a2 = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const float Kc = in[img + c];
+      const float dk = Kc - Kg;  // x - Kg = (x - Kc) + dk
+      a1 += sm[c] + cnt * dk;
+      a2 += sm[C + c] + 2.f * dk * sm[c] + cnt * dk * dk;
+    }
+    float* o = partial + (((long long)n * slabs + slab) * G + g) * 2;
+    o[0] = a1; o[1] = a2;
   }
-  const float mean = block_sum(s, red) / (float)cnt;
-  float q = 0.f;
-  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const long long p = i / cpg; const int c = (int)(i % cpg);
-    const float d = base[p * C + c] - mean;
-    q += d * d;
-  }
-  const float var = block_sum(q, red) / (float)cnt;
-  if (threadIdx.x == 0) {
-    stats[((long long)n * G + g) * 2 + 0] = mean;
+}
+
+__global__ void groupnorm_finalize_kernel(const float* __restrict__ in, const float* __restrict__ partial,
+                                          float* __restrict__ stats, int HW, int C, int G, int slabs, float eps) {
+  const int n = blockIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int s = 0; s < slabs; ++s) {
+      const float* o = partial + (((long long)n * slabs + s) * G + g) * 2;
+      a1 += o[0]; a2 += o[1];
+    }
+    const int cpg = C / G;
+    const float cnt = (float)HW * cpg;
+    const float Kg = in[(long long)n * HW * C + g * cpg];
+    const float m1 = a1 / cnt;
+    const float var = fmaxf(a2 / cnt - m1 * m1, 0.f);
+    stats[((long long)n * G + g) * 2 + 0] = Kg + m1;
     stats[((long long)n * G + g) * 2 + 1] = rsqrtf(var + eps);
   }
 }
@@ -365,19 +420,148 @@ __global__ void groupnorm_apply_kernel(const float4* __restrict__ in, float4* __
   }
 }
 
+static int groupnorm_stats_launch(const float* in, float* stats, int N, int HW, int C, int groups, float eps,
+                                  cudaStream_t st) {
+  // scratch layout: [N*G*2 final stats][N*slabs*G*2 partials]
+  int slabs = (int)std::min<long long>(GN_MAX_SLABS, std::max<long long>(1, (148LL * 4) / std::max(N, 1)));
+  slabs = std::min(slabs, std::max(1, HW / 16));
+  float* partial = stats + (long long)N * groups * 2;
+  groupnorm_partial_kernel<<<dim3(slabs, N), GN_THREADS, 2 * C * sizeof(float), st>>>(in, partial, HW, C, groups, slabs);
+  int rc = check_launch("groupnorm_partial");
+  if (rc) return rc;
+  groupnorm_finalize_kernel<<<N, 32, 0, st>>>(in, partial, stats, HW, C, groups, slabs, eps);
+  return check_launch("groupnorm_finalize");
+}
+
+extern "C" long long mmvid_groupnorm_scratch_floats(int N, int groups) {
+  return (long long)N * groups * 2 * (1 + GN_MAX_SLABS);
+}
+
+extern "C" int mmvid_groupnorm_stats(const float* in, float* stats, int N, int HW, int C, int groups, float eps,
+                                     mmvid_stream_t stream) {
+  MMVID_REQUIRE(C % groups == 0 && C % 4 == 0 && C <= 1024, "C divisible by groups and 4, <= 1024");
+  if (N == 0) return MMVID_OK;
+  return groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, to_stream(stream));
+}
+
 extern "C" int mmvid_groupnorm(const float* in, float* out, const float* gamma, const float* beta, float* stats,
                                int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream) {
-  MMVID_REQUIRE(C % groups == 0 && C % 4 == 0, "C divisible by groups and 4");
+  MMVID_REQUIRE(C % groups == 0 && C % 4 == 0 && C <= 1024, "C divisible by groups and 4, <= 1024");
   if (N == 0) return MMVID_OK;
   cudaStream_t st = to_stream(stream);
-  groupnorm_stats_kernel<<<dim3(groups, N), 512, 0, st>>>(in, stats, HW, C, groups, eps);
-  int rc = check_launch("groupnorm_stats");
+  int rc = groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, st);
   if (rc) return rc;
   const long long total4 = (long long)N * HW * (C / 4);
   const int blocks = (int)std::min<long long>(ceil_div<long long>(total4, 256), 148 * 16);
   groupnorm_apply_kernel<<<blocks, 256, 0, st>>>((const float4*)in, (float4*)out, gamma, beta, stats, HW, C, groups,
                                                   swish, total4);
   return check_launch("groupnorm_apply");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder tail, fused:  GroupNorm-apply + swish + 3x3 conv to <= 4 output channels + clamp/rescale, NCHW out
+// (Decoder.norm_out -> nonlinearity -> conv_out, model.py:578-581, + vae.py:55).  The generic implicit GEMM wastes
+// a 64-wide N tile on 3 output channels and the normalised activation would make an extra 2x-tensor HBM round
+// trip; here the raw activation is read once (halo tile in smem, normalised on the fly) and 3 floats/pixel leave.
+// Block = 16 x 32 output pixels, 256 threads, each thread owns 2 pixels; channels are processed 32 at a time.
+// ------------------------------------------------------------------------------------------------
+constexpr int CO_TH = 16, CO_TW = 32, CO_CH = 32, CO_LD = 36;
+
+__global__ void __launch_bounds__(256) conv_out_fused_kernel(const float* __restrict__ in, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ w /*[Cout][3][3][C]*/,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            int H, int W, int C, int G, int Cout, int post_clamp) {
+  extern __shared__ float smem[];
+  float* tile = smem;                                   // [(CO_TH+2)*(CO_TW+2)][CO_LD]
+  float* wsm = smem + (CO_TH + 2) * (CO_TW + 2) * CO_LD;  // [4][9][CO_CH]
+  const int n = blockIdx.z, y0 = blockIdx.y * CO_TH, x0 = blockIdx.x * CO_TW;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps: rows ty and ty+8
+  const int cpg = C / G;
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int HP = CO_TH + 2, WP = CO_TW + 2;
+  for (int c0 = 0; c0 < C; c0 += CO_CH) {
+    __syncthreads();
+    // halo tile, normalised + swish on load; zero outside the image (conv padding applies to the activated tensor)
+    for (int i = threadIdx.x; i < HP * WP * (CO_CH / 4); i += 256) {
+      const int c4 = i % (CO_CH / 4), p = i / (CO_CH / 4);
+      const int py = p / WP, px = p - py * WP;
+      const int y = y0 + py - 1, x = x0 + px - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        v = *reinterpret_cast<const float4*>(in + (((long long)n * H + y) * W + x) * C + c0 + c4 * 4);
+        float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + c4 * 4 + j, g = c / cpg;
+          const float mean = stats[((long long)n * G + g) * 2], rstd = stats[((long long)n * G + g) * 2 + 1];
+          float t = (r[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+          r[j] = t / (1.f + expf(-t));
+        }
+        v = make_float4(r[0], r[1], r[2], r[3]);
+      }
+      *reinterpret_cast<float4*>(tile + (size_t)p * CO_LD + c4 * 4) = v;
+    }
+    for (int i = threadIdx.x; i < 4 * 9 * CO_CH; i += 256) {
+      const int c = i % CO_CH, tap = (i / CO_CH) % 9, co = i / (CO_CH * 9);
+      wsm[i] = co < Cout ? w[((long long)co * 9 + tap) * C + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const float* a0 = tile + (size_t)((ty + ky) * WP + tx + kx) * CO_LD;
+      const float* a1 = tile + (size_t)((ty + 8 + ky) * WP + tx + kx) * CO_LD;
+#pragma unroll
+      for (int c4 = 0; c4 < CO_CH / 4; ++c4) {
+        const float4 p0 = *reinterpret_cast<const float4*>(a0 + c4 * 4);
+        const float4 p1 = *reinterpret_cast<const float4*>(a1 + c4 * 4);
+#pragma unroll
+        for (int co = 0; co < 4; ++co) {
+          const float4 wv = *reinterpret_cast<const float4*>(wsm + (co * 9 + tap) * CO_CH + c4 * 4);
+          acc[0][co] = fmaf(p0.x, wv.x, acc[0][co]); acc[0][co] = fmaf(p0.y, wv.y, acc[0][co]);
+          acc[0][co] = fmaf(p0.z, wv.z, acc[0][co]); acc[0][co] = fmaf(p0.w, wv.w, acc[0][co]);
+          acc[1][co] = fmaf(p1.x, wv.x, acc[1][co]); acc[1][co] = fmaf(p1.y, wv.y, acc[1][co]);
+          acc[1][co] = fmaf(p1.z, wv.z, acc[1][co]); acc[1][co] = fmaf(p1.w, wv.w, acc[1][co]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int y = y0 + ty + i * 8, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    for (int co = 0; co < Cout; ++co) {
+      float v = acc[i][co] + (bias ? bias[co] : 0.f);
+      if (post_clamp) v = (fminf(fmaxf(v, -1.f), 1.f) + 1.f) * 0.5f;
+      out[(((long long)n * Cout + co) * H + y) * W + x] = v;  // NCHW: a warp writes 32 consecutive x
+    }
+  }
+}
+
+extern "C" int mmvid_conv_out_fused(const float* in, const float* gamma, const float* beta, const float* w,
+                                    const float* bias, float* out, float* stats_scratch, int N, int H, int W, int C,
+                                    int Cout, int groups, float eps, int post_clamp, mmvid_stream_t stream) {
+  MMVID_REQUIRE(Cout >= 1 && Cout <= 4, "1..4 output channels");
+  MMVID_REQUIRE(C % CO_CH == 0 && C % groups == 0, "C multiple of 32 and of groups");
+  if (N == 0) return MMVID_OK;
+  cudaStream_t st = to_stream(stream);
+  int rc = groupnorm_stats_launch(in, stats_scratch, N, H * W, C, groups, eps, st);
+  if (rc) return rc;
+  const size_t smem = ((size_t)(CO_TH + 2) * (CO_TW + 2) * CO_LD + 4 * 9 * CO_CH) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_out_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  dim3 grid(ceil_div(W, CO_TW), ceil_div(H, CO_TH), N);
+  conv_out_fused_kernel<<<grid, 256, smem, st>>>(in, stats_scratch, gamma, beta, w, bias, out, H, W, C, groups, Cout,
+                                                 post_clamp);
+  return check_launch("conv_out_fused");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -25,6 +25,26 @@ constexpr int BQ = 128, BKV = 128, HD = 64;
 constexpr int TMEM_COLS = 256;
 constexpr int O_COL = 128;
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// (x0, x1) * s + b with one packed FFMA2
+__device__ __forceinline__ void ffma2(float x0, float x1, float s, float b, float& y0, float& y1) {
+  unsigned long long px, ps, pb, py;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(px) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ps) : "f"(s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(py) : "l"(px), "l"(ps), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(py));
+}
+
 struct AttArgs {
   void* out; long long ldo; int out_bf16;
   int B, H, S, S_pad, mask_kind;
@@ -155,74 +175,91 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_tc_kernel(const __gr
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
       const int kv0 = j * BKV;
+      // warp-uniform: does every row of this warp see all 128 keys of the tile?  (true for all interior tiles of
+      // the bidirectional BERT mask; false only on the padded last tile, causal diagonals and the two special rows)
+      const bool tile_full = __all_sync(0xffffffffu, (kv0 >= lo) && (kv0 + BKV <= hi));
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // pass 1: row max over visible keys
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int ch = 0; ch < BKV / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(t_row + ch * 32, r);
-        tmem_ld_wait();
+      // ---- pass 1: row max (64 columns in flight per wait)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = kv0 + ch * 32 + i;
-          const float s = (col >= lo && col < hi) ? __uint_as_float(r[i]) : -INFINITY;
-          mx = fmaxf(mx, s);
+      for (int ch = 0; ch < BKV / 32; ++ch) {
+        uint32_t r0[32];
+        tmem_ld32(t_row + ch * 32, r0);
+        tmem_ld_wait();
+        if (tile_full) {
+          float m0 = __uint_as_float(r0[0]), m1 = __uint_as_float(r0[1]);
+#pragma unroll
+          for (int i = 2; i < 32; i += 4) {
+            m0 = fmax3(m0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+            if (i + 3 < 32) m1 = fmax3(m1, __uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3]));
+          }
+          mx = fmax3(mx, m0, m1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c0 = kv0 + ch * 32 + i;
+            mx = fmaxf(mx, (c0 >= lo && c0 < hi) ? __uint_as_float(r0[i]) : -INFINITY);
+          }
         }
       }
       const float m_new = fmaxf(m, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f((m - m_use) * c);  // m = -inf -> 0
-      const float mc = m_use * c;
-      float rs = 0.f;
-      // pass 2: P = exp2(s*c - m*c) written in place
+      const float alpha = ex2_approx((m - m_use) * c);  // m = -inf -> 0
+      const float nmc = -m_use * c;
+      float rs0 = 0.f, rs1 = 0.f;
+      // ---- pass 2: P = exp2(s*c - m*c), written back in place
 #pragma unroll 1
       for (int ch = 0; ch < BKV / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(t_row + ch * 32, r);
         tmem_ld_wait();
-        float p[32];
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = kv0 + ch * 32 + i;
-          const float e = exp2f(fmaf(__uint_as_float(r[i]), c, -mc));
-          p[i] = (col >= lo && col < hi) ? e : 0.f;
-        }
-        if constexpr (TF32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { rs += p[i]; r[i] = __float_as_uint(p[i]); }
-          tmem_st32(t_row + ch * 32, r);
-        } else {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            __nv_bfloat162 v2 = __floats2bfloat162_rn(p[2 * i], p[2 * i + 1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&v2);
-            // accumulate the row sum from the ROUNDED probabilities so numerator and denominator agree
-            rs += __bfloat162float(v2.x) + __bfloat162float(v2.y);
+        for (int i = 0; i < 32; i += 2) {
+          float a0, a1;
+          ffma2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), c, nmc, a0, a1);
+          float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+          if (!tile_full) {
+            const int col = kv0 + ch * 32 + i;
+            e0 = (col >= lo && col < hi) ? e0 : 0.f;
+            e1 = (col + 1 >= lo && col + 1 < hi) ? e1 : 0.f;
           }
-          tmem_st16(t_row + ch * 16, pk);
+          if constexpr (TF32) {
+            rs0 += e0; rs1 += e1;
+            r[i] = __float_as_uint(e0); r[i + 1] = __float_as_uint(e1);
+          } else {
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(e0, e1);
+            const uint32_t w = *reinterpret_cast<uint32_t*>(&v2);
+            pk[i >> 1] = w;
+            // row sum from the ROUNDED probabilities so numerator and denominator agree
+            rs0 += __uint_as_float(w << 16);
+            rs1 += __uint_as_float(w & 0xffff0000u);
+          }
         }
+        if constexpr (TF32) tmem_st32(t_row + ch * 32, r);
+        else tmem_st16(t_row + ch * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
-      l = l * alpha + rs;
+      l = l * alpha + (rs0 + rs1);
       m = m_new;
-      // O_j
+      // ---- O_j
       mbar_wait(o_full, ph);
       tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < HD / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(t_row + O_COL + ch * 32, r);
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r0[32];
+        tmem_ld32(t_row + O_COL + hf * 32, r0);
         tmem_ld_wait();
+        if (hf == 1) {
+          tc_fence_before();
+          mbar_arrive(o_free);  // O_j is in registers: the next QK^T may overwrite S/P, the next PV may overwrite O
+        }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[ch * 32 + i] = fmaf(o[ch * 32 + i], alpha, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) o[hf * 32 + i] = fmaf(o[hf * 32 + i], alpha, __uint_as_float(r0[i]));
       }
-      tc_fence_before();
-      mbar_arrive(o_free);
     }
     // ---- normalise, stage through (dead) tile smem, coalesced store
     const float inv = 1.f / l;

@@ -1,11 +1,11 @@
 // tcgen05 GEMM for every Linear / 1x1 conv of the hot path (MMVID_TF32 and MMVID_BF16 precision):
 //     C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual)
-// Warp-specialised, one 128 x BN output tile per CTA, 2 CTAs co-resident per SM so one CTA's epilogue
-// overlaps the other's main loop:
-//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 3-stage smem ring, mbarrier full/empty
-//   warp 1      MMA issuer     one elected thread issues tcgen05.mma (kind::tf32 | kind::f16), accumulator in TMEM
-//   warps 2..5  epilogue       tcgen05.ld TMEM -> registers -> padded smem -> fully coalesced global stores with
-//                              bias / QuickGELU / residual fused (fp32 or bf16 output)
+// Persistent and warp-specialised: one CTA per SM walks 128 x BN output tiles (BN = 256 / 128 / 64):
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4..8-stage smem ring, mbarrier full/empty
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma (kind::tf32 | kind::f16) into one of TWO TMEM
+//                              accumulators, so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2..5  epilogue       tcgen05.ld TMEM -> registers -> per-warp smem transpose -> 128-byte coalesced global
+//                              stores with bias / QuickGELU / residual fused (fp32 or bf16 output)
 // Both operands are K-major (activations [M,K] row-major, nn.Linear weights [N,K] row-major), so a single
 // descriptor flavour is needed.  fp32 operands are loaded with the TFLOAT32 tensor-map type (round-to-nearest
 // to tf32 inside the TMA unit); M/N/K tails rely on TMA zero fill, stores are predicated.
@@ -13,6 +13,7 @@
 #include "tc_common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 using namespace mmvid;
 using namespace mmvid::tc;
@@ -58,8 +59,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, con
 namespace {
 
 constexpr int BM = 128;
-constexpr int STAGES = 3;
 constexpr int GEMM_THREADS = 192;
+constexpr int EPI_LD = 36;  // floats per staged row (32 + 4 pad: conflict-free 128-bit writes and reads)
 
 struct EpiArgs {
   const float* bias;
@@ -72,49 +73,66 @@ struct EpiArgs {
   int N, K, act;
   // implicit-GEMM conv (CONV=true): 128-pixel M tile = box {BW, BH, BNI} of the NHWC input, K = (tap, channel block)
   int cCin, cKW, cPadT, cPadL, cBW, cBH, cBNI, cW, cH;
+  int num_m_tiles, num_n_tiles;
+  int raster;  // 0: m fastest; 1: n fastest; 2: 8-wide n groups (each wave covers ~8 weight tiles x ~18 row tiles)
 };
+
+// tile index -> (m tile, n tile)
+__device__ __forceinline__ void tile_coords(const EpiArgs& e, int tile, int& mt, int& nt) {
+  if (e.raster == 0) { mt = tile % e.num_m_tiles; nt = tile / e.num_m_tiles; }
+  else if (e.raster == 1) { nt = tile % e.num_n_tiles; mt = tile / e.num_n_tiles; }
+  else {
+    const int GW = 8;
+    const int group_tiles = GW * e.num_m_tiles;
+    const int g = tile / group_tiles, r = tile - g * group_tiles;
+    const int n_first = g * GW;
+    const int gw = min(GW, e.num_n_tiles - n_first);
+    nt = n_first + r % gw;
+    mt = r / gw;
+  }
+}
+
+template <int BN>
+constexpr int gemm_stages() { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
 
 template <int BN>
 constexpr size_t gemm_smem_bytes() {
-  return (size_t)STAGES * (BM * 128 + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return (size_t)gemm_stages<BN>() * (BM * 128 + BN * 128) + 4 * 32 * EPI_LD * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
+// Persistent, warp-specialised tcgen05 GEMM.  grid = min(#tiles, #SMs); every CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so concurrently running CTAs share the same weight
+// tile in L2).  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue), tile loop.
 template <bool TF32, int BN, bool CONV>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmB, EpiArgs e) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB, EpiArgs e) {
+  constexpr int STAGES = gemm_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
-  // carve: [barriers 256 B][pad to 1024][stages: A | B]
+  // carve: [barriers 256 B][pad to 1024][stages: A | B][epilogue staging]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int BKE = TF32 ? 32 : 64;  // elements per 128-byte k-block
+  float* epi_stage = reinterpret_cast<float*>(tiles + (size_t)STAGES * STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int num_k = (e.K + BKE - 1) / BKE;
-  // conv: decompose the tile's first pixel into (image, row, col); tiles never straddle rows partially because
-  // BW = min(W,128), BH = min(H, 128/BW), BNI = 128/(BW*BH) and W, H are powers of two
-  int cx0 = 0, cy0 = 0, cn0 = 0, cblocks = 1;
-  if constexpr (CONV) {
-    const long long pix = (long long)m0;
-    cx0 = (int)(pix % e.cW);
-    cy0 = (int)((pix / e.cW) % e.cH);
-    cn0 = (int)(pix / ((long long)e.cW * e.cH));
-    cblocks = e.cCin / BKE;
-  }
+  const int total_tiles = e.num_m_tiles * e.num_n_tiles;
+  const int cblocks = CONV ? e.cCin / BKE : 1;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, BN);
+    tmem_alloc(tmem_ptr, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -124,121 +142,184 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
 
   if (warp == 0) {
     if (elect_one()) {
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        uint8_t* a = tiles + s * STAGE_BYTES;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, nt;
+        tile_coords(e, tile, mt, nt);
+        const int m0 = mt * BM, n0 = nt * BN;
+        int cx0 = 0, cy0 = 0, cn0 = 0;
         if constexpr (CONV) {
-          const int tap = kb / cblocks, cb = kb - tap * cblocks;
-          const int ky = tap / e.cKW, kx = tap - ky * e.cKW;
-          // halo taps use negative / past-the-edge coordinates: TMA zero-fills, which IS the conv zero padding
-          tma_load_4d(a, &tmA, &full[s], cb * BKE, cx0 + kx - e.cPadL, cy0 + ky - e.cPadT, cn0);
-        } else {
-          tma_load_2d(a, &tmA, &full[s], kb * BKE, m0);
+          // tiles never straddle rows partially: BW = min(W,128), BH = min(H,128/BW), BNI = 128/(BW*BH), W,H powers of 2
+          cx0 = m0 % e.cW;
+          cy0 = (m0 / e.cW) % e.cH;
+          cn0 = m0 / (e.cW * e.cH);
         }
-        tma_load_2d(a + A_BYTES, &tmB, &full[s], kb * BKE, n0);
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* a = tiles + s * STAGE_BYTES;
+          if constexpr (CONV) {
+            const int tap = kb / cblocks, cb = kb - tap * cblocks;
+            const int ky = tap / e.cKW, kx = tap - ky * e.cKW;
+            // halo taps use negative / past-the-edge coordinates: TMA zero-fills, which IS the conv zero padding
+            tma_load_4d(a, &tmA, &full[s], cb * BKE, cx0 + kx - e.cPadL, cy0 + ky - e.cPadT, cn0);
+          } else {
+            tma_load_2d(a, &tmA, &full[s], kb * BKE, m0);
+          }
+          tma_load_2d(a + A_BYTES, &tmB, &full[s], kb * BKE, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<TF32>(BM, BN);
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
-        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-        const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // 4 x 32 bytes = UMMA_K (8 tf32 | 16 bf16) per instruction
-          mma_ss<TF32>(tmem_base, desc_advance(a_desc, kk * 32), desc_advance(b_desc, kk * 32), idesc,
-                       (kb | kk) != 0 ? 1u : 0u);
-        tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+          for (int kk = 0; kk < 4; ++kk)  // 4 x 32 bytes = UMMA_K (8 tf32 | 16 bf16) per instruction
+            mma_ss<TF32>(d_tmem, desc_advance(a_desc, kk * 32), desc_advance(b_desc, kk * 32), idesc,
+                         (kb | kk) != 0 ? 1u : 0u);
+          tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete
       }
-      tc_commit(tmem_full);    // accumulator complete
     }
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4
     const int q = warp & 3;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    constexpr int LDS = BN + 4;
-    float* stage = reinterpret_cast<float*>(tiles);  // pipeline buffers are dead now
-    float* my_rows = stage + (size_t)(q * 32) * LDS;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(my_rows + (size_t)lane * LDS + c * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                             __uint_as_float(r[4 * j + 3]));
-    }
-    __syncwarp();
+    float* st = epi_stage + (size_t)q * 32 * EPI_LD;
     const bool vec_ok = (e.N % 4 == 0) && (e.ldc % 4 == 0) && (!e.residual || e.ldr % 4 == 0);
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      int mt, nt;
+      tile_coords(e, tile, mt, nt);
+      const int m0 = mt * BM, n0 = nt * BN;
+      const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_src = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int r = 0; r < 32; ++r) {
-      const long long m = (long long)m0 + q * 32 + r;
-      if (m >= e.M) break;
-      const float* srow = my_rows + (size_t)r * LDS;
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= e.N) break;
+        uint32_t r[32];
+        tmem_ld32(t_src + c * 32, r);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(st + (size_t)lane * EPI_LD);
 #pragma unroll
-      for (int cc = 0; cc < BN / 128 + (BN % 128 != 0); ++cc) {
-        const int col = cc * 128 + lane * 4;
-        if (col >= BN) continue;
-        const int n = n0 + col;
-        if (n >= e.N) continue;
-        float4 v = *reinterpret_cast<const float4*>(srow + col);
-        float o[4] = {v.x, v.y, v.z, v.w};
-        if (vec_ok) {
-          if (e.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-            o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
-          }
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        // coalesced phase: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+        const int col = (lane & 7) * 4;
+        const int n = n0 + c * 32 + col;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias && n < e.N) {
+          if (vec_ok) bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+          else { bv.x = e.bias[n]; if (n + 1 < e.N) bv.y = e.bias[n + 1]; if (n + 2 < e.N) bv.z = e.bias[n + 2]; if (n + 3 < e.N) bv.w = e.bias[n + 3]; }
+        }
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          const int rl = r0 + (lane >> 3);
+          const long long m = (long long)m0 + q * 32 + rl;
+          if (m >= e.M || n >= e.N) continue;
+          const float4 v = *reinterpret_cast<const float4*>(st + (size_t)rl * EPI_LD + col);
+          float o[4] = {v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], e.act);
-          if (e.residual) {
-            const float4 rr = *reinterpret_cast<const float4*>(e.residual + m * e.ldr + n);
-            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-          }
-          if (e.c_bf16) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + m * e.ldc + n) = pk;
+          if (vec_ok) {
+            if (e.residual) {
+              const float4 rr = *reinterpret_cast<const float4*>(e.residual + m * e.ldr + n);
+              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+            }
+            if (e.c_bf16) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + m * e.ldc + n) = pk;
+            } else {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+            }
           } else {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n + j >= e.N) break;
-            float x = o[j];
-            if (e.bias) x += e.bias[n + j];
-            x = apply_act(x, e.act);
-            if (e.residual) x += e.residual[m * e.ldr + n + j];
-            if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.C)[m * e.ldc + n + j] = __float2bfloat16_rn(x);
-            else reinterpret_cast<float*>(e.C)[m * e.ldc + n + j] = x;
+            for (int j = 0; j < 4; ++j) {
+              if (n + j >= e.N) break;
+              float x = o[j];
+              if (e.residual) x += e.residual[m * e.ldr + n + j];
+              if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.C)[m * e.ldc + n + j] = __float2bfloat16_rn(x);
+              else reinterpret_cast<float*>(e.C)[m * e.ldc + n + j] = x;
+            }
           }
         }
+        __syncwarp();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// pick the N tile that minimises (#rounds over the SMs) x (tile width): larger tiles halve the L2->SM operand
+// traffic per FLOP, smaller ones quantise better on small problems
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+int pick_bn(long long M, int N) {
+  const int forced = env_int("MMVID_GEMM_BN", 0);  // tuning / experiments only
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  const int sms = num_sms();
+  const long long mt = ceil_div<long long>(M, BM);
+  int best = 64;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long tiles = mt * ceil_div(N, bn);
+    const double rounds = (double)ceil_div<long long>(tiles, sms);
+    const double per_tile = bn + (bn == 64 ? 24 : (bn == 128 ? 12 : 0));  // small tiles pay more L2 traffic / overhead
+    const double cost = rounds * per_tile;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 template <bool TF32, int BN, bool CONV = false>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs& e, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = gemm_smem_bytes<BN>();
   if (!attr_set) {
@@ -246,9 +327,20 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs& e, cud
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(err));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div<long long>(e.M, BM), (unsigned)ceil_div(e.N, BN));
+  e.num_m_tiles = (int)ceil_div<long long>(e.M, BM);
+  e.num_n_tiles = ceil_div(e.N, BN);
+  e.raster = env_int("MMVID_GEMM_RASTER", 0);
+  const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   gemm_tc_kernel<TF32, BN, CONV><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, e);
   return check_launch("gemm_tc");
+}
+
+template <bool TF32, bool CONV>
+int launch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs& e, cudaStream_t st) {
+  if (BN == 256) return launch<TF32, 256, CONV>(tmA, tmB, e, st);
+  if (BN == 128) return launch<TF32, 128, CONV>(tmA, tmB, e, st);
+  return launch<TF32, 64, CONV>(tmA, tmB, e, st);
 }
 
 }  // namespace
@@ -266,8 +358,7 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
   if (M == 0 || N == 0) return MMVID_OK;
   const int BKE = tf32 ? 32 : 64;
   // tile width: keep >= ~1.5 waves of CTAs on 148 SMs (2 CTAs/SM) when the problem is small
-  const long long tiles128 = ceil_div<long long>(M, BM) * ceil_div(N, 128);
-  const int BN = (tiles128 < 200) ? 64 : 128;
+  const int BN = pick_bn(M, N);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -283,9 +374,8 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
     int rc = make_tensor_map(&tmB, W, w_dtype, 2, dims, str, box);
     if (rc) return rc;
   }
-  EpiArgs e{bias, residual, ldr, C, ldc, c_dtype == MMVID_DT_BF16, M, N, K, act, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (tf32) return BN == 64 ? launch<true, 64>(tmA, tmB, e, st) : launch<true, 128>(tmA, tmB, e, st);
-  return BN == 64 ? launch<false, 64>(tmA, tmB, e, st) : launch<false, 128>(tmA, tmB, e, st);
+  EpiArgs e{bias, residual, ldr, C, ldc, c_dtype == MMVID_DT_BF16, M, N, K, act, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  return tf32 ? launch_bn<true, false>(BN, tmA, tmB, e, st) : launch_bn<false, false>(BN, tmA, tmB, e, st);
 }
 
 
@@ -316,8 +406,7 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
     int rc = make_tensor_map(&tmA, p->in, MMVID_DT_F32, 4, dims, str, box);
     if (rc) return rc;
   }
-  const long long tiles128 = ceil_div<long long>(M, BM) * ceil_div(p->Cout, 128);
-  const int BN = (tiles128 < 200) ? 64 : 128;
+  const int BN = pick_bn(M, p->Cout);
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)p->Cout};
     uint64_t str[1] = {(uint64_t)K * 4};
@@ -326,6 +415,6 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
     if (rc) return rc;
   }
   EpiArgs e{p->bias, p->residual, (long long)p->Cout, p->out, (long long)p->Cout, 0, M, p->Cout, K, MMVID_ACT_NONE,
-            p->Cin, p->KW, p->pad_t, p->pad_l, BW, BH, BNI, p->W, p->H};
-  return BN == 64 ? launch<true, 64, true>(tmA, tmB, e, st) : launch<true, 128, true>(tmA, tmB, e, st);
+            p->Cin, p->KW, p->pad_t, p->pad_l, BW, BH, BNI, p->W, p->H, 0, 0, 0};
+  return launch_bn<true, true>(BN, tmA, tmB, e, st);
 }

@@ -112,7 +112,7 @@ def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None):
     assert x_nhwc.is_contiguous()
     N, H, W, Cc = x_nhwc.shape
     out = torch.empty_like(x_nhwc) if out is None else out
-    stats = torch.empty(N * groups * 2, device=x_nhwc.device, dtype=torch.float32)
+    stats = torch.empty(int(lib.mmvid_groupnorm_scratch_floats(N, groups)), device=x_nhwc.device, dtype=torch.float32)
     L.check(lib.mmvid_groupnorm(_ptr(x_nhwc), _ptr(out), _ptr(weight), _ptr(bias), _ptr(stats), N, H * W, Cc, groups,
                                 eps, int(swish), _stream()), "groupnorm")
     return out
@@ -296,4 +296,20 @@ def upsample2x(x):
     N, H, W, Cc = x.shape
     out = torch.empty(N, 2 * H, 2 * W, Cc, device=x.device, dtype=torch.float32)
     L.check(lib.mmvid_upsample2x(_ptr(x), _ptr(out), N, H, W, Cc, _stream()), "upsample2x")
+    return out
+
+
+def conv_out_fused(x_nhwc, gamma, beta, w_packed, bias, groups=32, eps=1e-6, post_clamp=True):
+    """GroupNorm + swish + 3x3 conv (Cout <= 4) + clamp/rescale; NHWC float32 in, NCHW out."""
+    lib = L.load()
+    _req(x_nhwc, torch.float32)
+    assert x_nhwc.is_contiguous() and w_packed.is_contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    Cout = w_packed.shape[0]
+    assert tuple(w_packed.shape[1:]) == (3, 3, Cc)
+    out = torch.empty(N, Cout, H, W, device=x_nhwc.device, dtype=torch.float32)
+    stats = torch.empty(int(lib.mmvid_groupnorm_scratch_floats(N, groups)), device=x_nhwc.device, dtype=torch.float32)
+    L.check(lib.mmvid_conv_out_fused(_ptr(x_nhwc), _ptr(gamma), _ptr(beta), _ptr(w_packed), _ptr(bias), _ptr(out),
+                                     _ptr(stats), N, H, W, Cc, Cout, groups, eps, int(post_clamp), _stream()),
+            "conv_out_fused")
     return out

@@ -286,8 +286,9 @@ class VQGanVAE1024(nn.Module):
                     h = self._attnblock(h, up.attn[bi])
             if lvl != 0:
                 h = self._conv3(h, up.upsample.conv, upsample=True)  # nearest x2 folded into the gather (model.py:56-62)
-        h = ops.groupnorm(h, dec.norm_out.weight, dec.norm_out.bias, swish=True, out=h)
-        return self._conv3(h, dec.conv_out, out_nchw=True, post_clamp=True)
+        # norm_out -> swish -> conv_out -> clamp/rescale in one pass over the 128-channel activation
+        return ops.conv_out_fused(h, dec.norm_out.weight, dec.norm_out.bias, self._pack.conv(dec.conv_out.weight),
+                                  dec.conv_out.bias, post_clamp=True)
 
     @torch.no_grad()
     def decode(self, img_seq):

@@ -188,6 +188,21 @@ def test_groupnorm_swish(C, HW):
     assert relerr(ops.groupnorm(x_nhwc, w, b, swish=True).permute(0, 3, 1, 2), ref * torch.sigmoid(ref)) < 5e-6
 
 
+def test_conv_out_fused_matches_groupnorm_swish_conv_clamp():
+    """Decoder tail (model.py:578-581 + vae.py:55) in one kernel vs the torch composition."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    for (N, C, H, W) in ((2, 128, 32, 32), (1, 128, 64, 64), (3, 128, 16, 48)):
+        x = (torch.randn(N, C, H, W, generator=g) * 1.5 + 0.3).cuda()
+        gw, gb = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+        w = (torch.randn(3, C, 3, 3, generator=g) / 10).cuda()
+        b = torch.randn(3, generator=g).cuda()
+        h = F.group_norm(x, 32, gw, gb, 1e-6)
+        ref = (F.conv2d(h * torch.sigmoid(h), w, b, padding=1).clamp(-1, 1) + 1) * 0.5
+        out = ops.conv_out_fused(x.permute(0, 2, 3, 1).contiguous(), gw, gb, w.permute(0, 2, 3, 1).contiguous(), b)
+        assert out.shape == ref.shape and relerr(out, ref) < 1e-5
+
+
 def _pack(w):
     return w.permute(0, 2, 3, 1).contiguous()
 
