@@ -14,6 +14,7 @@
 // V is consumed transposed (V^T[d, s], written by the QKV split) so every operand is K-major.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 using namespace mmvid;
 using namespace mmvid::tc;
@@ -322,6 +323,10 @@ int launch_att(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
 
 }  // namespace
 
+extern "C" int mmvid_attention_v3(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
+                                  int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
+                                  const int* host_prev_rows, int n_prev, int tf32, cudaStream_t st);
+
 extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, void* out, int out_dtype, long long ldo,
                                int B, int H, int S, int S_pad, int mask_kind, const int* host_prev_rows, int n_prev,
                                int precision, mmvid_stream_t stream) {
@@ -348,6 +353,13 @@ extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, voi
     uint32_t box[2] = {BKE, 64};
     int rc = make_tensor_map(&tv, vt, dt, 2, dims, str, box);
     if (rc) return rc;
+  }
+  {
+    // default: two-tile ping-pong kernel (tc_attention2.cu); MMVID_ATT_IMPL=1 selects the one-tile kernel below
+    const char* impl = getenv("MMVID_ATT_IMPL");
+    if (!(impl && impl[0] == '1'))
+      return mmvid_attention_v3(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind,
+                                host_prev_rows, n_prev, tf32 ? 1 : 0, to_stream(stream));
   }
   AttArgs a{};
   a.out = out; a.ldo = ldo; a.out_bf16 = out_dtype == MMVID_DT_BF16;

@@ -1,0 +1,353 @@
+// Flash attention v3 for sm_100a: TWO 128-query tiles per CTA ping-pong through the tensor core
+// (FA4-style schedule) so that the MMA pipe and the softmax (MUFU/FMA) pipes overlap inside one SM:
+//
+//   tensor core :  QK_A0 QK_B0 | PV_A0 QK_A1 PV_B0 QK_B1 | PV_A1 QK_A2 PV_B1 QK_B2 | ...
+//   softmax grp A:        [ P_A0 ......... ][O_A0][ P_A1 ......... ][O_A1] ...
+//   softmax grp B:              [ P_B0 ......... ][O_B0][ P_B1 ......... ][O_B1] ...
+//
+// One CTA per SM, 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 4-7 softmax group A, warps 8-11
+// group B (warp % 4 == TMEM lane quarter).  K / V^T tiles are double-buffered and shared by both query tiles
+// (half the L2 operand traffic of the one-tile kernel).  TMEM: S_A [0,128) S_B [128,256) O_A [256,320)
+// O_B [320,384).  Softmax, masking and the in-place P write-back are identical to tc_attention.cu.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace mmvid;
+using namespace mmvid::tc;
+
+namespace {
+
+constexpr int ATT2_THREADS = 384;
+constexpr int BQ = 128, BKV = 128, HD = 64;
+constexpr int TMEM_COLS = 512;
+__host__ __device__ constexpr int S_COL_OF(int g) { return g * 128; }
+__host__ __device__ constexpr int O_COL_OF(int g) { return 256 + g * 64; }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void ffma2(float x0, float x1, float s, float b, float& y0, float& y1) {
+  unsigned long long px, ps, pb, py;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(px) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ps) : "f"(s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(py) : "l"(px), "l"(ps), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(py));
+}
+
+struct Att2Args {
+  void* out; long long ldo; int out_bf16;
+  int B, H, S, S_pad, mask_kind;
+  int prev_rows[4]; int n_prev;
+};
+
+template <bool TF32>
+constexpr size_t att2_smem_bytes() {
+  // Q_A, Q_B, 2 x K, 2 x V^T tiles (each BQ*HD elements) + barriers + alignment slack
+  return (size_t)6 * (TF32 ? 32768 : 16384) + 1024 + 256;
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                       const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmV, Att2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]  (count 2: QK_A and QK_B both read the stage)
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]  (count 2)
+  uint64_t* s_full = bars + 9;    // [2] per group
+  uint64_t* p_ready = bars + 11;  // [2]
+  uint64_t* o_full = bars + 13;   // [2]
+  uint64_t* o_free = bars + 15;   // [2]
+  uint64_t* all_done = bars + 17;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~(uintptr_t)1023);
+  constexpr int ESZ = TF32 ? 4 : 2;
+  constexpr int BKE = 128 / ESZ;
+  constexpr int QK_KB = HD / BKE;   // 2 | 1
+  constexpr int PV_KB = BKV / BKE;  // 4 | 2
+  constexpr int T_BYTES = BQ * HD * ESZ;  // every tile (Q, K, V^T) has the same byte size
+  uint8_t* sQ[2] = {tiles, tiles + T_BYTES};
+  uint8_t* sK[2] = {tiles + 2 * T_BYTES, tiles + 3 * T_BYTES};
+  uint8_t* sV[2] = {tiles + 4 * T_BYTES, tiles + 5 * T_BYTES};
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * BQ);
+  const int bh = blockIdx.y;
+  const int b = bh / a.H, h = bh - b * a.H;
+  int n_kv = (a.S + BKV - 1) / BKV;
+  if (a.mask_kind == MMVID_MASK_CAUSAL) n_kv = min(n_kv, (q0 + 2 * BQ - 1) / BKV + 1);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 128);
+    }
+    mbar_init(all_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * T_BYTES);
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int kb = 0; kb < QK_KB; ++kb)
+          tma_load_2d(sQ[g] + kb * (BQ * 128), &tmQ, q_full, kb * BKE, bh * a.S_pad + q0 + g * BQ);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], T_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < QK_KB; ++kb)
+          tma_load_2d(sK[st] + kb * (BKV * 128), &tmK, &k_full[st], kb * BKE, bh * a.S_pad + j * BKV);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], T_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < PV_KB; ++kb)
+          tma_load_2d(sV[st] + kb * (HD * 128), &tmV, &v_full[st], j * BKV + kb * BKE, bh * HD);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc<TF32>(BQ, BKV);
+      constexpr uint32_t idesc_pv = make_idesc<TF32>(BQ, HD);
+      auto issue_qk = [&](int g, int st) {
+#pragma unroll
+        for (int kb = 0; kb < QK_KB; ++kb) {
+          const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ[g] + kb * (BQ * 128)));
+          const uint64_t kd = make_smem_desc_sw128(smem_u32(sK[st] + kb * (BKV * 128)));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ss<TF32>(tmem_base + S_COL_OF(g), desc_advance(qd, kk * 32), desc_advance(kd, kk * 32), idesc_qk,
+                         (kb | kk) != 0);
+        }
+        tc_commit(&k_empty[st]);
+        tc_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, int st) {
+#pragma unroll
+        for (int kb = 0; kb < PV_KB; ++kb) {
+          const uint64_t vd = make_smem_desc_sw128(smem_u32(sV[st] + kb * (HD * 128)));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ts<TF32>(tmem_base + O_COL_OF(g), tmem_base + S_COL_OF(g) + kb * 32 + kk * 8, desc_advance(vd, kk * 32), idesc_pv,
+                         (kb | kk) != 0);
+        }
+        tc_commit(&v_empty[st]);
+        tc_commit(&o_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t kvph = (j >> 1) & 1;   // phase of the K/V stage barriers
+        const uint32_t ph = j & 1;            // phase of the per-tile group barriers (one completion per kv tile)
+        const bool more = (j + 1 < n_kv);
+        mbar_wait(&v_full[st], kvph);
+        if (more) mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_ready[g], ph);                  // group g wrote P_j over S_g
+          if (j > 0) mbar_wait(&o_free[g], ph ^ 1);    // group g has O_{j-1} in registers
+          tc_fence_after();
+          issue_pv(g, st);
+          if (more) issue_qk(g, st ^ 1);               // S_g is free: PV_j (same issue stream) consumed P_j first
+        }
+      }
+      tc_commit(all_done);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax groups
+    const int g = (warp - 4) >> 2;  // 0: tile A, 1: tile B
+    const int qd = warp & 3;
+    const int row_local = qd * 32 + lane;
+    const int row = q0 + g * BQ + row_local;
+    const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const uint32_t t_s = t_row + S_COL_OF(g), t_o = t_row + O_COL_OF(g);
+    int lo = 0, hi = a.S;
+    if (a.mask_kind == MMVID_MASK_CAUSAL) hi = min(a.S, row + 1);
+    else if (a.mask_kind == MMVID_MASK_PREV) {
+      for (int i = 0; i < a.n_prev; ++i) if (a.prev_rows[i] == row) lo = row;
+    }
+    const float c = 0.125f * 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv0 = j * BKV;
+      const bool tile_full = __all_sync(0xffffffffu, (kv0 >= lo) && (kv0 + BKV <= hi));
+      mbar_wait(&s_full[g], ph);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < BKV / 32; ++ch) {
+        uint32_t r0[32];
+        tmem_ld32(t_s + ch * 32, r0);
+        tmem_ld_wait();
+        if (tile_full) {
+          float m0 = __uint_as_float(r0[0]), m1 = __uint_as_float(r0[1]);
+#pragma unroll
+          for (int i = 2; i < 32; i += 4) {
+            m0 = fmax3(m0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+            if (i + 3 < 32) m1 = fmax3(m1, __uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3]));
+          }
+          mx = fmax3(mx, m0, m1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c0 = kv0 + ch * 32 + i;
+            mx = fmaxf(mx, (c0 >= lo && c0 < hi) ? __uint_as_float(r0[i]) : -INFINITY);
+          }
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2_approx((m - m_use) * c);
+      const float nmc = -m_use * c;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < BKV / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(t_s + ch * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a0, a1;
+          ffma2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), c, nmc, a0, a1);
+          float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+          if (!tile_full) {
+            const int col = kv0 + ch * 32 + i;
+            e0 = (col >= lo && col < hi) ? e0 : 0.f;
+            e1 = (col + 1 >= lo && col + 1 < hi) ? e1 : 0.f;
+          }
+          if constexpr (TF32) {
+            rs0 += e0; rs1 += e1;
+            r[i] = __float_as_uint(e0); r[i + 1] = __float_as_uint(e1);
+          } else {
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(e0, e1);
+            const uint32_t w = *reinterpret_cast<uint32_t*>(&v2);
+            pk[i >> 1] = w;
+            rs0 += __uint_as_float(w << 16);
+            rs1 += __uint_as_float(w & 0xffff0000u);
+          }
+        }
+        if constexpr (TF32) tmem_st32(t_s + ch * 32, r);
+        else tmem_st16(t_s + ch * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[g]);
+      l = l * alpha + (rs0 + rs1);
+      m = m_new;
+      mbar_wait(&o_full[g], ph);
+      tc_fence_after();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r0[32];
+        tmem_ld32(t_o + hf * 32, r0);
+        tmem_ld_wait();
+        if (hf == 1) {
+          tc_fence_before();
+          mbar_arrive(&o_free[g]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[hf * 32 + i] = fmaf(o[hf * 32 + i], alpha, __uint_as_float(r0[i]));
+      }
+    }
+    // every MMA of BOTH groups must have retired before K/V smem is recycled as the output staging area
+    mbar_wait(all_done, 0);
+    const float inv = 1.f / l;
+    uint8_t* stage_base = g == 0 ? sK[0] : sV[0];  // 2 contiguous tiles each: >= 128 x 68 floats
+    const int q_tile0 = q0 + g * BQ;
+    if (a.out_bf16) {
+      constexpr int LD = HD + 8;
+      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage_base) + (size_t)row_local * LD;
+#pragma unroll
+      for (int i = 0; i < HD; i += 2)
+        *reinterpret_cast<__nv_bfloat162*>(st + i) = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv);
+      __syncwarp();
+      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+      for (int r0 = 0; r0 < 32; r0 += 4) {
+        const int rl = qd * 32 + r0 + (lane >> 3);
+        const int s = q_tile0 + rl;
+        if (s < a.S) {
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<__nv_bfloat16*>(stage_base) + (size_t)rl * LD + (lane & 7) * 8);
+          *reinterpret_cast<uint4*>(outp + ((long long)b * a.S + s) * a.ldo + h * HD + (lane & 7) * 8) = v;
+        }
+      }
+    } else {
+      constexpr int LD = HD + 4;
+      float* st = reinterpret_cast<float*>(stage_base) + (size_t)row_local * LD;
+#pragma unroll
+      for (int i = 0; i < HD; i += 4)
+        *reinterpret_cast<float4*>(st + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      __syncwarp();
+      float* outp = reinterpret_cast<float*>(a.out);
+      for (int r0 = 0; r0 < 32; r0 += 2) {
+        const int rl = qd * 32 + r0 + (lane >> 4);
+        const int s = q_tile0 + rl;
+        if (s < a.S) {
+          const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<float*>(stage_base) + (size_t)rl * LD + (lane & 15) * 4);
+          *reinterpret_cast<float4*>(outp + ((long long)b * a.S + s) * a.ldo + h * HD + (lane & 15) * 4) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+template <bool TF32>
+int launch_att2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Att2Args& a, cudaStream_t st) {
+  static bool attr_set = false;
+  constexpr size_t smem = att2_smem_bytes<TF32>();
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(attention_tc2_kernel<TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(attention_tc2): %s", cudaGetErrorString(err));
+    attr_set = true;
+  }
+  dim3 grid((a.S_pad / BQ + 1) / 2, a.B * a.H);
+  attention_tc2_kernel<TF32><<<grid, ATT2_THREADS, smem, st>>>(tq, tk, tv, a);
+  return check_launch("attention_tc2");
+}
+
+}  // namespace
+
+// called by mmvid_attention (tc_attention.cu) unless MMVID_ATT_IMPL=1 selects the one-tile kernel
+extern "C" int mmvid_attention_v3(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
+                                  int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
+                                  const int* host_prev_rows, int n_prev, int tf32, cudaStream_t st) {
+  Att2Args a{};
+  a.out = out; a.ldo = ldo; a.out_bf16 = out_bf16;
+  a.B = B; a.H = H; a.S = S; a.S_pad = S_pad; a.mask_kind = mask_kind; a.n_prev = n_prev;
+  for (int i = 0; i < n_prev; ++i) a.prev_rows[i] = host_prev_rows[i];
+  return tf32 ? launch_att2<true>(*tq, *tk, *tv, a, st) : launch_att2<false>(*tq, *tk, *tv, a, st);
+}

@@ -201,65 +201,96 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4
     const int q = warp & 3;
-    float* st = epi_stage + (size_t)q * 32 * EPI_LD;
+    const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(q * 32 * EPI_LD * 4);
+    const uint32_t st_wr = st_base + (uint32_t)(lane * EPI_LD * 4);                       // my row while transposing
+    const int col = (lane & 7) * 4, rsub = lane >> 3;                                     // coalesced phase mapping
+    const uint32_t st_rd = st_base + (uint32_t)((rsub * EPI_LD + col) * 4);
     const bool vec_ok = (e.N % 4 == 0) && (e.ldc % 4 == 0) && (!e.residual || e.ldr % 4 == 0);
+    constexpr int NCH = BN / 32;
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       int mt, nt;
       tile_coords(e, tile, mt, nt);
       const int m0 = mt * BM, n0 = nt * BN;
       const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+      // bias for every chunk of this tile is fetched BEFORE waiting for the accumulator (latency off the critical path)
+      float4 bias_r[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int n = n0 + c * 32 + col;
+        bias_r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias && n < e.N) {
+          if (vec_ok) bias_r[c] = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+          else {
+            bias_r[c].x = e.bias[n];
+            if (n + 1 < e.N) bias_r[c].y = e.bias[n + 1];
+            if (n + 2 < e.N) bias_r[c].z = e.bias[n + 2];
+            if (n + 3 < e.N) bias_r[c].w = e.bias[n + 3];
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_src = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      const long long m_first = (long long)m0 + q * 32 + rsub;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         if (n0 + c * 32 >= e.N) break;
         uint32_t r[32];
         tmem_ld32(t_src + c * 32, r);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(st + (size_t)lane * EPI_LD);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
+          sts128(st_wr + j * 16, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                 __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        // coalesced phase: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-        const int col = (lane & 7) * 4;
         const int n = n0 + c * 32 + col;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias && n < e.N) {
-          if (vec_ok) bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-          else { bv.x = e.bias[n]; if (n + 1 < e.N) bv.y = e.bias[n + 1]; if (n + 2 < e.N) bv.z = e.bias[n + 2]; if (n + 3 < e.N) bv.w = e.bias[n + 3]; }
-        }
+        const bool n_ok = n < e.N;
+        if (vec_ok) {
+          // 8 lanes cover one 128-byte row segment, 4 rows per instruction; all loads are issued before any store
+          float4 res[8], v[8];
+          if (e.residual) {
 #pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += 4) {
-          const int rl = r0 + (lane >> 3);
-          const long long m = (long long)m0 + q * 32 + rl;
-          if (m >= e.M || n >= e.N) continue;
-          const float4 v = *reinterpret_cast<const float4*>(st + (size_t)rl * EPI_LD + col);
-          float o[4] = {v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], e.act);
-          if (vec_ok) {
-            if (e.residual) {
-              const float4 rr = *reinterpret_cast<const float4*>(e.residual + m * e.ldr + n);
-              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+            for (int i = 0; i < 8; ++i) {
+              const long long m = m_first + i * 4;
+              res[i] = (m < e.M && n_ok) ? *reinterpret_cast<const float4*>(e.residual + m * e.ldr + n)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (e.c_bf16) {
-              __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + m * e.ldc + n) = pk;
-            } else {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          } else {
+          }
 #pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = lds128(st_rd + (uint32_t)(i * 4 * EPI_LD * 4));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long m = m_first + i * 4;
+            float o[4] = {v[i].x + bias_r[c].x, v[i].y + bias_r[c].y, v[i].z + bias_r[c].z, v[i].w + bias_r[c].w};
+            if (e.act != MMVID_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], e.act);
+            }
+            if (e.residual) { o[0] += res[i].x; o[1] += res[i].y; o[2] += res[i].z; o[3] += res[i].w; }
+            if (m < e.M && n_ok) {
+              if (e.c_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + m * e.ldc + n) = pk;
+              } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+              }
+            }
+          }
+        } else {
+          // unaligned N / leading dimensions: scalar path
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const long long m = m_first + i * 4;
+            if (m >= e.M || !n_ok) continue;
+            const float4 v = lds128(st_rd + (uint32_t)(i * 4 * EPI_LD * 4));
+            const float o[4] = {v.x + bias_r[c].x, v.y + bias_r[c].y, v.z + bias_r[c].z, v.w + bias_r[c].w};
             for (int j = 0; j < 4; ++j) {
               if (n + j >= e.N) break;
-              float x = o[j];
+              float x = apply_act(o[j], e.act);
               if (e.residual) x += e.residual[m * e.ldr + n + j];
               if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.C)[m * e.ldc + n + j] = __float2bfloat16_rn(x);
               else reinterpret_cast<float*>(e.C)[m * e.ldc + n + j] = x;

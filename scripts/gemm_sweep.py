@@ -27,9 +27,10 @@ for (M,N,K,name) in json.loads(sys.argv[2]):
     res[name]=(round(tot/10*1000,1), round(2*M*N*K/(tot/10)/1e9,1), round(warm*1000,1), round(2*M*N*K/warm/1e9,1))
 print(json.dumps(res))
 '''
+QUICK = "--quick" in sys.argv
 for prec in ("tf32", "bf16"):
-    for bn in (64, 128, 256):
-        for raster in (0, 1, 2):
+    for bn in ((128, 256) if QUICK else (64, 128, 256)):
+        for raster in ((0, 1) if QUICK else (0, 1, 2)):
             env = dict(os.environ, MMVID_GEMM_BN=str(bn), MMVID_GEMM_RASTER=str(raster))
             r = subprocess.run([sys.executable, "-c", CHILD, prec, json.dumps(SHAPES)], env=env, capture_output=True, text=True, timeout=300)
             print(prec, "BN", bn, "raster", raster, r.stdout.strip() or r.stderr[-500:], flush=True)
