@@ -102,6 +102,12 @@ int mmvid_softmax_rows(float* scores, long long batch, int rows, int cols, long 
 int mmvid_attention(const void* q, const void* k, const void* vt, void* out, int out_dtype, long long ldo,
                     int B, int H, int S, int S_pad, int mask_kind, const int* host_prev_rows, int n_prev,
                     int precision, mmvid_stream_t stream);
+/* Fused QKV projection (nn.MultiheadAttention in-proj, clip_model.py:208,222): A[B*S, H*64] . W[3*H*64, H*64]^T + b
+ * scattered by the GEMM epilogue into q,k [B,H,S_pad,64] and vt [B,H,64,S_pad] (fp32 for TF32, bf16 for BF16).
+ * Padding (rows >= S) is not written: keep the buffers zero-initialised. */
+int mmvid_linear_qkv(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
+                     const float* bias, void* q, void* k, void* vt, int out_dtype, int B, int H, int S, int S_pad,
+                     int precision, mmvid_stream_t stream);
 /* qkv [B*S, 3*H*64] fp32 -> q,k [B,H,S_pad,64], vt [B,H,64,S_pad] in fp32 or bf16 (zero padded) */
 int mmvid_qkv_split(const float* qkv, void* q, void* k, void* vt, int dtype, int B, int H, int S, int S_pad,
                     mmvid_stream_t stream);
@@ -176,6 +182,30 @@ int mmvid_nhwc_to_nchw(const float* in, float* out, int N, int C, int HW, mmvid_
  * (dalle_bert.py:527-531 `logits + temperature * gumbel`), temperature applied by caller via noise scale */
 int mmvid_softmax_logits(const float* logits, const float* noise, float noise_scale, float* probs, long long rows,
                          int n, mmvid_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training path (BERT.forward(return_loss=True), dalle_bert.py:980-1127; optimiser loop train.py:320-325).
+ * GEMM-shaped backward work reuses mmvid_linear / mmvid_gemm_batched_f32 on transposed operands; these are the
+ * HBM-bound backward pieces.
+ * ---------------------------------------------------------------------------------------------- */
+int mmvid_act_forward(const float* z, float* y, long long n, int act, mmvid_stream_t stream);
+int mmvid_act_backward(const float* z, const float* dy, float* dz, long long n, int act, mmvid_stream_t stream);
+/* out[c] (+)= sum_r x[r, c]; scratch >= 64*cols floats; deterministic two-stage reduction (bias gradients) */
+int mmvid_colsum(const float* x, float* out, float* scratch, long long rows, int cols, int accumulate,
+                 mmvid_stream_t stream);
+/* LayerNorm backward: dx, and xhat*dy rows (dgamma = colsum(xhat_dy), dbeta = colsum(dy)) */
+int mmvid_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx, float* xhat_dy,
+                             long long rows, int D, float eps, mmvid_stream_t stream);
+/* in place: dp[r,c] = p[r,c] * (dp[r,c] - sum_c' dp[r,c'] p[r,c']) * scale */
+int mmvid_softmax_backward(const float* p, float* dp, long long rows, int cols, long long ld, float scale,
+                           mmvid_stream_t stream);
+/* F.cross_entropy over selected rows (dalle_bert.py:1040): loss_rows[r] = lse - logit[target], dlogits = softmax - onehot */
+int mmvid_cross_entropy(const float* logits, const int64_t* target, const uint8_t* sel, float* dlogits,
+                        float* loss_rows, long long rows, int n, mmvid_stream_t stream);
+/* embedding backward (scatter-add with atomics) for one gather segment */
+int mmvid_embed_backward(const float* dx, int B, int S, int D, const mmvid_embed_segment* host_segment, float* d_table,
+                         float* d_table2, float* d_pos, mmvid_stream_t stream);
+int mmvid_transpose2d(const float* in, float* out, int R, int C, mmvid_stream_t stream);
 
 #ifdef __cplusplus
 }

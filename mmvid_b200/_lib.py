@@ -42,6 +42,7 @@ SIGNATURES = {
                                     _f, _p]),
     "mmvid_softmax_rows": (_i, [_p, _ll, _i, _i, _ll, _i, _p, _i, _p]),
     "mmvid_attention": (_i, [_p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i, _p]),
+    "mmvid_linear_qkv": (_i, [_p, _i, _ll, _p, _i, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mmvid_qkv_split": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mmvid_decode_attention": (_i, [_p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _p]),
     "mmvid_linear_small_m": (_i, [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p]),
@@ -57,6 +58,14 @@ SIGNATURES = {
     "mmvid_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _p]),
     "mmvid_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _p]),
     "mmvid_softmax_logits": (_i, [_p, _p, _f, _p, _ll, _i, _p]),
+    "mmvid_act_forward": (_i, [_p, _p, _ll, _i, _p]),
+    "mmvid_act_backward": (_i, [_p, _p, _p, _ll, _i, _p]),
+    "mmvid_colsum": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
+    "mmvid_layernorm_backward": (_i, [_p, _p, _p, _p, _p, _ll, _i, _f, _p]),
+    "mmvid_softmax_backward": (_i, [_p, _p, _ll, _i, _ll, _f, _p]),
+    "mmvid_cross_entropy": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p]),
+    "mmvid_embed_backward": (_i, [_p, _i, _i, _i, C.POINTER(EmbedSegment), _p, _p, _p, _p]),
+    "mmvid_transpose2d": (_i, [_p, _p, _i, _i, _p]),
 }
 
 _lib = None

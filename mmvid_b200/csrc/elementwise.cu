@@ -688,3 +688,228 @@ extern "C" int mmvid_codebook_gather(const int64_t* ids, const float* codebook, 
       ids, (const float4*)codebook, (float4*)out, T, dim / 4);
   return check_launch("codebook_gather");
 }
+
+// ================================================================================================
+// Training-path kernels (BERT.forward(return_loss=True), dalle_bert.py:980-1127): elementwise / reduction
+// backward pieces.  The GEMM-shaped backward work reuses mmvid_linear / mmvid_gemm_batched_f32.
+// ================================================================================================
+
+// y = act(z) elementwise (kept separate from the GEMM in training so z is available to the backward)
+__global__ void act_fwd_kernel(const float4* __restrict__ z, float4* __restrict__ y, long long n4, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = z[i];
+    v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+    y[i] = v;
+  }
+}
+// dz = dy * act'(z);  QuickGELU: s = sigmoid(1.702 z), d = s + 1.702 z s (1 - s)
+__global__ void act_bwd_kernel(const float4* __restrict__ z, const float4* __restrict__ dy, float4* __restrict__ dz,
+                               long long n4, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = z[i], g = dy[i];
+    float zz[4] = {a.x, a.y, a.z, a.w}, gg[4] = {g.x, g.y, g.z, g.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float k = act == MMVID_ACT_QUICKGELU ? 1.702f : 1.f;
+      const float s = 1.f / (1.f + expf(-k * zz[j]));
+      const float d = act == MMVID_ACT_NONE ? 1.f : s + k * zz[j] * s * (1.f - s);
+      o[j] = gg[j] * d;
+    }
+    dz[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+extern "C" int mmvid_act_forward(const float* z, float* y, long long n, int act, mmvid_stream_t stream) {
+  MMVID_REQUIRE(n % 4 == 0, "n multiple of 4");
+  if (n == 0) return MMVID_OK;
+  const int blocks = (int)std::min<long long>(ceil_div<long long>(n / 4, 256), 148 * 16);
+  act_fwd_kernel<<<blocks, 256, 0, to_stream(stream)>>>((const float4*)z, (float4*)y, n / 4, act);
+  return check_launch("act_forward");
+}
+extern "C" int mmvid_act_backward(const float* z, const float* dy, float* dz, long long n, int act,
+                                  mmvid_stream_t stream) {
+  MMVID_REQUIRE(n % 4 == 0, "n multiple of 4");
+  if (n == 0) return MMVID_OK;
+  const int blocks = (int)std::min<long long>(ceil_div<long long>(n / 4, 256), 148 * 16);
+  act_bwd_kernel<<<blocks, 256, 0, to_stream(stream)>>>((const float4*)z, (const float4*)dy, (float4*)dz, n / 4, act);
+  return check_launch("act_backward");
+}
+
+// column sums: out[c] = sum_r x[r, c]   (bias gradients).  Two-stage, deterministic.
+__global__ void colsum_partial_kernel(const float* __restrict__ x, float* __restrict__ part, long long rows, int cols,
+                                      int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += x[r * cols + c];
+  part[(long long)blockIdx.y * cols + c] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int cols,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(long long)p * cols + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+extern "C" int mmvid_colsum(const float* x, float* out, float* scratch /* >= 64*cols floats */, long long rows, int cols,
+                            int accumulate, mmvid_stream_t stream) {
+  if (cols == 0) return MMVID_OK;
+  const int nparts = (int)std::max<long long>(1, std::min<long long>(64, rows / 64));
+  const int rpb = (int)ceil_div<long long>(rows, nparts);
+  cudaStream_t st = to_stream(stream);
+  colsum_partial_kernel<<<dim3(ceil_div(cols, 128), nparts), 128, 0, st>>>(x, scratch, rows, cols, rpb);
+  int rc = check_launch("colsum_partial");
+  if (rc) return rc;
+  colsum_final_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(scratch, out, nparts, cols, accumulate);
+  return check_launch("colsum_final");
+}
+
+// LayerNorm backward (one warp per row): dx, and per-block partial dgamma/dbeta reduced by mmvid_colsum-like stage
+template <int VEC_PER_LANE>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ dgb_rows,
+                                     long long rows, int D, float eps) {
+  // dgb_rows: [rows, 2*D] would be too large; instead each row writes xhat*dy and dy into dx-sized scratch handled by caller
+  const int wpb = blockDim.x >> 5;
+  const long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nvec = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const float4* gr = reinterpret_cast<const float4*>(dy + row * D);
+  float4 v[VEC_PER_LANE], g[VEC_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) { v[i] = xr[c]; g[i] = gr[c]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    else { v[i] = make_float4(0, 0, 0, 0); g[i] = v[i]; }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float qv = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) { float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean; qv += (a * a + b * b) + (cc * cc + d * d); }
+  }
+  const float rstd = rsqrtf(warp_sum(qv) / (float)D + eps);
+  // s1 = sum(g*gamma), s2 = sum(g*gamma*xhat)
+  float s1 = 0.f, s2 = 0.f;
+  const float4* gm = reinterpret_cast<const float4*>(gamma);
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 w = __ldg(gm + c);
+      const float xh[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+      const float gg[4] = {g[i].x * w.x, g[i].y * w.y, g[i].z * w.z, g[i].w * w.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s1 += gg[j]; s2 += gg[j] * xh[j]; }
+    }
+  }
+  s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
+  float4* dxr = reinterpret_cast<float4*>(dx + row * D);
+  float4* dgr = reinterpret_cast<float4*>(dgb_rows + row * D);  // xhat * dy, summed over rows by the caller -> dgamma
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 w = __ldg(gm + c);
+      const float xh[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+      const float gy[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+      const float ww[4] = {w.x, w.y, w.z, w.w};
+      float o[4], t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { o[j] = rstd * (gy[j] * ww[j] - s1 - xh[j] * s2); t[j] = gy[j] * xh[j]; }
+      dxr[c] = make_float4(o[0], o[1], o[2], o[3]);
+      dgr[c] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  }
+}
+extern "C" int mmvid_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx,
+                                        float* xhat_dy /* [rows, D] scratch: dgamma = colsum(xhat_dy), dbeta = colsum(dy) */,
+                                        long long rows, int D, float eps, mmvid_stream_t stream) {
+  MMVID_REQUIRE(D % 4 == 0 && D <= 1024, "D multiple of 4, <= 1024");
+  if (rows == 0) return MMVID_OK;
+  layernorm_bwd_kernel<8><<<(unsigned)ceil_div<long long>(rows, 8), 256, 0, to_stream(stream)>>>(x, gamma, dy, dx, xhat_dy,
+                                                                                                rows, D, eps);
+  return check_launch("layernorm_backward");
+}
+
+// softmax backward in place: ds[r, c] = p[r, c] * (dp[r, c] - sum_c' dp[r, c'] p[r, c']) * scale
+__global__ void softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, int cols, long long ld, float scale) {
+  __shared__ float red[32];
+  const long long r = blockIdx.x;
+  const float* pr = p + r * ld;
+  float* dr = dp + r * ld;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) s += pr[c] * dr[c];
+  s = block_sum(s, red);
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) dr[c] = pr[c] * (dr[c] - s) * scale;
+}
+extern "C" int mmvid_softmax_backward(const float* p, float* dp, long long rows, int cols, long long ld, float scale,
+                                      mmvid_stream_t stream) {
+  if (rows == 0) return MMVID_OK;
+  softmax_bwd_kernel<<<(unsigned)rows, 256, 0, to_stream(stream)>>>(p, dp, cols, ld, scale);
+  return check_launch("softmax_backward");
+}
+
+// cross entropy over selected rows (F.cross_entropy(logits[~mask1], target[~mask1]), dalle_bert.py:1040):
+//   loss_sum += lse(row) - row[target];  dlogits[row] = (softmax(row) - onehot) * sel[row]   (scaled by caller via grad_scale)
+__global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                                  const uint8_t* __restrict__ sel, float* __restrict__ dlogits,
+                                  float* __restrict__ loss_rows, int n) {
+  __shared__ float red[32];
+  const long long r = blockIdx.x;
+  const float* l = logits + r * n;
+  float* d = dlogits + r * n;
+  if (!sel[r]) {
+    for (int c = threadIdx.x; c < n; c += blockDim.x) d[c] = 0.f;
+    if (threadIdx.x == 0) loss_rows[r] = 0.f;
+    return;
+  }
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) m = fmaxf(m, l[c]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) s += expf(l[c] - m);
+  s = block_sum(s, red);
+  const float lse = m + logf(s);
+  const int t = (int)target[r];
+  for (int c = threadIdx.x; c < n; c += blockDim.x) d[c] = expf(l[c] - lse) - (c == t ? 1.f : 0.f);
+  if (threadIdx.x == 0) loss_rows[r] = lse - l[t];
+}
+extern "C" int mmvid_cross_entropy(const float* logits, const int64_t* target, const uint8_t* sel, float* dlogits,
+                                   float* loss_rows, long long rows, int n, mmvid_stream_t stream) {
+  if (rows == 0) return MMVID_OK;
+  ce_fwd_bwd_kernel<<<(unsigned)rows, 256, 0, to_stream(stream)>>>(logits, target, sel, dlogits, loss_rows, n);
+  return check_launch("cross_entropy");
+}
+
+// embedding backward: d_table[id] += dx[b, seq_off+i]; d_table2[id] += ...; d_pos[i] += ...   (atomics: training only)
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, int S, int D, mmvid_embed_segment g, float* d_table,
+                                 float* d_table2, float* d_pos) {
+  const int r = blockIdx.x, b = blockIdx.y;
+  long long id = g.ids[(long long)b * g.ids_bstride + r];
+  if (g.use_pad && id == g.pad_value) id = g.pad_base + r;
+  const float* src = dx + ((long long)b * S + g.seq_off + r) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = src[c];
+    if (d_table) atomicAdd(d_table + id * (long long)D + c, v);
+    if (d_table2) atomicAdd(d_table2 + id * (long long)D + c, v);
+    if (d_pos) atomicAdd(d_pos + (long long)r * D + c, v);
+  }
+}
+extern "C" int mmvid_embed_backward(const float* dx, int B, int S, int D, const mmvid_embed_segment* seg, float* d_table,
+                                    float* d_table2, float* d_pos, mmvid_stream_t stream) {
+  if (B == 0 || seg->n == 0) return MMVID_OK;
+  embed_bwd_kernel<<<dim3(seg->n, B), 192, 0, to_stream(stream)>>>(dx, S, D, *seg, d_table, d_table2, d_pos);
+  return check_launch("embed_backward");
+}
+
+// 2-D transpose [R, C] -> [C, R] (weight / activation transposes feeding the backward GEMMs)
+extern "C" int mmvid_transpose2d(const float* in, float* out, int R, int Cn, mmvid_stream_t stream) {
+  dim3 grid(ceil_div(Cn, 32), ceil_div(R, 32), 1);
+  transpose_kernel<<<grid, dim3(32, 8), 0, to_stream(stream)>>>(in, out, R, Cn);
+  return check_launch("transpose2d");
+}

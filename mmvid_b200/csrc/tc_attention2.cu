@@ -5,8 +5,10 @@
 //   softmax grp A:        [ P_A0 ......... ][O_A0][ P_A1 ......... ][O_A1] ...
 //   softmax grp B:              [ P_B0 ......... ][O_B0][ P_B1 ......... ][O_B1] ...
 //
-// One CTA per SM, 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 4-7 softmax group A, warps 8-11
-// group B (warp % 4 == TMEM lane quarter).  K / V^T tiles are double-buffered and shared by both query tiles
+// One CTA per SM, 384 threads = 3 warpgroups: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} shrinks to 56
+// registers/thread with setmaxnreg.dec, the two softmax warpgroups (A: warps 4-7, B: warps 8-11) grow to 224 so a
+// whole 128-column score row lives in registers (the register file is partitioned per SM sub-partition: 3 warps x 32
+// lanes x (56 + 224 + 224) = 16128 <= 16384).  K / V^T tiles are double-buffered and shared by both query tiles
 // (half the L2 operand traffic of the one-tile kernel).  TMEM: S_A [0,128) S_B [128,256) O_A [256,320)
 // O_B [320,384).  Softmax, masking and the in-place P write-back are identical to tc_attention.cu.
 #include "common.cuh"
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(q_full, 2 * T_BYTES);
@@ -144,14 +147,14 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
         tc_commit(&k_empty[st]);
         tc_commit(&s_full[g]);
       };
-      auto issue_pv = [&](int g, int st) {
+      auto issue_pv = [&](int g, int st, bool first_tile) {
 #pragma unroll
         for (int kb = 0; kb < PV_KB; ++kb) {
           const uint64_t vd = make_smem_desc_sw128(smem_u32(sV[st] + kb * (HD * 128)));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
+          for (int kk = 0; kk < 4; ++kk)  // O accumulates in TMEM over ALL kv tiles (lazy rescale, see softmax warps)
             mma_ts<TF32>(tmem_base + O_COL_OF(g), tmem_base + S_COL_OF(g) + kb * 32 + kk * 8, desc_advance(vd, kk * 32), idesc_pv,
-                         (kb | kk) != 0);
+                         (!first_tile || (kb | kk) != 0) ? 1u : 0u);
         }
         tc_commit(&v_empty[st]);
         tc_commit(&o_full[g]);
@@ -170,10 +173,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
         if (more) mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_ready[g], ph);                  // group g wrote P_j over S_g
-          if (j > 0) mbar_wait(&o_free[g], ph ^ 1);    // group g has O_{j-1} in registers
+          mbar_wait(&p_ready[g], ph);                  // group g wrote P_j over S_g (and rescaled O_g if it had to)
           tc_fence_after();
-          issue_pv(g, st);
+          issue_pv(g, st, j == 0);
           if (more) issue_qk(g, st ^ 1);               // S_g is free: PV_j (same issue stream) consumed P_j first
         }
       }
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax groups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int g = (warp - 4) >> 2;  // 0: tile A, 1: tile B
     const int qd = warp & 3;
     const int row_local = qd * 32 + lane;
@@ -192,11 +195,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
     else if (a.mask_kind == MMVID_MASK_PREV) {
       for (int i = 0; i < a.n_prev; ++i) if (a.prev_rows[i] == row) lo = row;
     }
-    const float c = 0.125f * 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e): scores are handled in the log2 domain
+    // Lazy rescale (FA4): O_g accumulates in TMEM across kv tiles relative to a reference max m_ref that is only moved
+    // when the running row max exceeds it by more than 2^8 (P <= 256 is harmless in fp32/tf32/bf16).  The per-tile
+    // critical path is then  S -> P  only: no O round trip through registers, and the whole 128-column score row
+    // lives in registers between ONE tcgen05.wait::ld and ONE tcgen05.wait::st.
+    constexpr float RESCALE_THRESH = 8.f;
+    float m_ref = -INFINITY, l = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
@@ -204,52 +209,64 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
       const bool tile_full = __all_sync(0xffffffffu, (kv0 >= lo) && (kv0 + BKV <= hi));
       mbar_wait(&s_full[g], ph);
       tc_fence_after();
-      float mx = -INFINITY;
+      uint32_t r[4][32];
 #pragma unroll
-      for (int ch = 0; ch < BKV / 32; ++ch) {
-        uint32_t r0[32];
-        tmem_ld32(t_s + ch * 32, r0);
-        tmem_ld_wait();
-        if (tile_full) {
-          float m0 = __uint_as_float(r0[0]), m1 = __uint_as_float(r0[1]);
+      for (int ch = 0; ch < 4; ++ch) tmem_ld32(t_s + ch * 32, r[ch]);
+      tmem_ld_wait();
+      if (!tile_full) {
 #pragma unroll
-          for (int i = 2; i < 32; i += 4) {
-            m0 = fmax3(m0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
-            if (i + 3 < 32) m1 = fmax3(m1, __uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3]));
-          }
-          mx = fmax3(mx, m0, m1);
-        } else {
+        for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int c0 = kv0 + ch * 32 + i;
-            mx = fmaxf(mx, (c0 >= lo && c0 < hi) ? __uint_as_float(r0[i]) : -INFINITY);
+            const int col = kv0 + ch * 32 + i;
+            if (!(col >= lo && col < hi)) r[ch][i] = 0xff800000u;  // -inf
           }
+      }
+      float mx0 = __uint_as_float(r[0][0]), mx1 = __uint_as_float(r[0][1]);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int i = (ch == 0 ? 2 : 0); i < 32; i += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
+          if (i + 3 < 32) mx1 = fmax3(mx1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+        }
+      const float mx = fmaxf(mx0, mx1);
+      // move the reference only when needed (warp-uniform decision because TMEM ld/st are warp collectives)
+      const bool need = (mx != -INFINITY) && (m_ref == -INFINITY || (mx - m_ref) * c > RESCALE_THRESH);
+      float alpha = 1.f;
+      bool resc = false;
+      if (need) {
+        if (m_ref != -INFINITY) { alpha = ex2_approx((m_ref - mx) * c); resc = true; }  // else: O row and l are still 0
+        m_ref = mx;
+      }
+      if (__any_sync(0xffffffffu, resc)) {
+        // rare path: O_g *= alpha in TMEM (alpha = 1 for rows that keep their reference).  PV_{j-1} must have retired.
+        mbar_wait(&o_full[g], ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t t[32];
+          tmem_ld32(t_o + hf * 32, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+          tmem_st32(t_o + hf * 32, t);
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2_approx((m - m_use) * c);
-      const float nmc = -m_use * c;
+      l *= alpha;
+      const float nmc = (m_ref == -INFINITY) ? 0.f : -m_ref * c;
       float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < BKV / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(t_s + ch * 32, r);
-        tmem_ld_wait();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float a0, a1;
-          ffma2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), c, nmc, a0, a1);
-          float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-          if (!tile_full) {
-            const int col = kv0 + ch * 32 + i;
-            e0 = (col >= lo && col < hi) ? e0 : 0.f;
-            e1 = (col + 1 >= lo && col + 1 < hi) ? e1 : 0.f;
-          }
+          ffma2(__uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]), c, nmc, a0, a1);
+          const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);  // exp2(-inf) = 0 for masked keys
           if constexpr (TF32) {
             rs0 += e0; rs1 += e1;
-            r[i] = __float_as_uint(e0); r[i + 1] = __float_as_uint(e1);
+            r[ch][i] = __float_as_uint(e0); r[ch][i + 1] = __float_as_uint(e1);
           } else {
             __nv_bfloat162 v2 = __floats2bfloat162_rn(e0, e1);
             const uint32_t w = *reinterpret_cast<uint32_t*>(&v2);
@@ -258,31 +275,26 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
             rs1 += __uint_as_float(w & 0xffff0000u);
           }
         }
-        if constexpr (TF32) tmem_st32(t_s + ch * 32, r);
+        if constexpr (TF32) tmem_st32(t_s + ch * 32, r[ch]);
         else tmem_st16(t_s + ch * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[g]);
-      l = l * alpha + (rs0 + rs1);
-      m = m_new;
-      mbar_wait(&o_full[g], ph);
-      tc_fence_after();
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t r0[32];
-        tmem_ld32(t_o + hf * 32, r0);
-        tmem_ld_wait();
-        if (hf == 1) {
-          tc_fence_before();
-          mbar_arrive(&o_free[g]);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[hf * 32 + i] = fmaf(o[hf * 32 + i], alpha, __uint_as_float(r0[i]));
-      }
+      l += rs0 + rs1;
     }
     // every MMA of BOTH groups must have retired before K/V smem is recycled as the output staging area
     mbar_wait(all_done, 0);
+    tc_fence_after();
+    float o[HD];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t t[32];
+      tmem_ld32(t_o + hf * 32, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[hf * 32 + i] = __uint_as_float(t[i]);
+    }
     const float inv = 1.f / l;
     uint8_t* stage_base = g == 0 ? sK[0] : sV[0];  // 2 contiguous tiles each: >= 128 x 68 floats
     const int q_tile0 = q0 + g * BQ;

@@ -4,7 +4,7 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4..8-stage smem ring, mbarrier full/empty
 //   warp 1      MMA issuer     one elected thread issues tcgen05.mma (kind::tf32 | kind::f16) into one of TWO TMEM
 //                              accumulators, so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..5  epilogue       tcgen05.ld TMEM -> registers -> per-warp smem transpose -> 128-byte coalesced global
+//   warps 2..9  epilogue       tcgen05.ld TMEM -> registers -> per-warp smem transpose -> 128-byte coalesced global
 //                              stores with bias / QuickGELU / residual fused (fp32 or bf16 output)
 // Both operands are K-major (activations [M,K] row-major, nn.Linear weights [N,K] row-major), so a single
 // descriptor flavour is needed.  fp32 operands are loaded with the TFLOAT32 tensor-map type (round-to-nearest
@@ -59,7 +59,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, con
 namespace {
 
 constexpr int BM = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 constexpr int EPI_LD = 36;  // floats per staged row (32 + 4 pad: conflict-free 128-bit writes and reads)
 
 struct EpiArgs {
@@ -74,6 +75,9 @@ struct EpiArgs {
   // implicit-GEMM conv (CONV=true): 128-pixel M tile = box {BW, BH, BNI} of the NHWC input, K = (tap, channel block)
   int cCin, cKW, cPadT, cPadL, cBW, cBH, cBNI, cW, cH;
   int num_m_tiles, num_n_tiles;
+  // QKV mode (qkv_q != nullptr): the [M, 3*H*64] result is scattered straight into the attention layout
+  //   Q,K -> [B,H,S_pad,64]   V -> V^T [B,H,64,S_pad]   (fp32 or bf16 via c_bf16); bias applied, no act/residual
+  void* qkv_q; void* qkv_k; void* qkv_vt; int qS, qSpad, qH;
   int raster;  // 0: m fastest; 1: n fastest; 2: 8-wide n groups (each wave covers ~8 weight tiles x ~18 row tiles)
 };
 
@@ -93,11 +97,11 @@ __device__ __forceinline__ void tile_coords(const EpiArgs& e, int tile, int& mt,
 }
 
 template <int BN>
-constexpr int gemm_stages() { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
+constexpr int gemm_stages() { return BN == 256 ? 3 : (BN == 128 ? 5 : 7); }
 
 template <int BN>
 constexpr size_t gemm_smem_bytes() {
-  return (size_t)gemm_stages<BN>() * (BM * 128 + BN * 128) + 4 * 32 * EPI_LD * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
+  return (size_t)gemm_stages<BN>() * (BM * 128 + BN * 128) + EPI_WARPS * 32 * EPI_LD * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 // Persistent, warp-specialised tcgen05 GEMM.  grid = min(#tiles, #SMs); every CTA walks tiles
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -199,19 +203,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4
+    // ---------------- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
     const int q = warp & 3;
-    const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(q * 32 * EPI_LD * 4);
+    const int ew = warp - 2;              // 0..7
+    const int chalf = ew >> 2;            // which half of the tile's 32-column chunks this warp drains
+    const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
     const uint32_t st_wr = st_base + (uint32_t)(lane * EPI_LD * 4);                       // my row while transposing
     const int col = (lane & 7) * 4, rsub = lane >> 3;                                     // coalesced phase mapping
     const uint32_t st_rd = st_base + (uint32_t)((rsub * EPI_LD + col) * 4);
     const bool vec_ok = (e.N % 4 == 0) && (e.ldc % 4 == 0) && (!e.residual || e.ldr % 4 == 0);
-    constexpr int NCH = BN / 32;
+    constexpr int NCH = BN / 64;          // chunks per warp (half of the tile's BN/32)
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       int mt, nt;
       tile_coords(e, tile, mt, nt);
-      const int m0 = mt * BM, n0 = nt * BN;
+      const int m0 = mt * BM, n0 = nt * BN + chalf * (BN / 2);
       const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
       // bias for every chunk of this tile is fetched BEFORE waiting for the accumulator (latency off the critical path)
       float4 bias_r[NCH];
@@ -231,14 +237,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      const uint32_t t_src = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
       const long long m_first = (long long)m0 + q * 32 + rsub;
+      // all of this warp's accumulator columns are requested back to back and awaited ONCE (a tcgen05.wait::ld per
+      // chunk costs a few hundred cycles of exposed latency)
+      uint32_t racc[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld32(t_src + c * 32, racc[c]);
+      tmem_ld_wait();
+      // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (n0 + c * 32 >= e.N) break;
-        uint32_t r[32];
-        tmem_ld32(t_src + c * 32, r);
-        tmem_ld_wait();
+        uint32_t (&r)[32] = racc[c];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           sts128(st_wr + j * 16, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -246,7 +260,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         __syncwarp();
         const int n = n0 + c * 32 + col;
         const bool n_ok = n < e.N;
-        if (vec_ok) {
+        if (e.qkv_q != nullptr) {
+          const int D = e.qH * 64;
+          const int nc = n0 + c * 32;               // first column of this chunk: never straddles a head (64-aligned)
+          const int which = nc / D, hh = (nc - which * D) >> 6, d0 = nc & 63;
+          if (which < 2) {
+            // Q / K: rows stay rows; 8 lanes x 16 B cover the chunk's 32 head-dim values of one token
+            void* dst = which == 0 ? e.qkv_q : e.qkv_k;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long long m = m_first + i * 4;
+              if (m >= e.M) continue;
+              const float4 v = lds128(st_rd + (uint32_t)(i * 4 * EPI_LD * 4));
+              const int bb = (int)(m / e.qS), ss = (int)(m - (long long)bb * e.qS);
+              const long long off = (((long long)bb * e.qH + hh) * e.qSpad + ss) * 64 + d0 + col;
+              const float o0 = v.x + bias_r[c].x, o1 = v.y + bias_r[c].y, o2 = v.z + bias_r[c].z, o3 = v.w + bias_r[c].w;
+              if (e.c_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + off) = pk;
+              } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + off) = make_float4(o0, o1, o2, o3);
+              }
+            }
+          } else {
+            // V: written transposed straight from the accumulator registers (lane == token row, so for a fixed
+            // head-dim index the 32 lanes write 32 consecutive tokens: one coalesced 128-byte (64-byte bf16) store)
+            const long long m = (long long)m0 + q * 32 + lane;
+            if (m < e.M) {
+              const int bb = (int)(m / e.qS), ss = (int)(m - (long long)bb * e.qS);
+              const long long base = (((long long)bb * e.qH + hh) * 64 + d0) * e.qSpad + ss;
+#pragma unroll
+              for (int d = 0; d < 32; ++d) {
+                const float o = __uint_as_float(r[d]) + (e.bias ? __ldg(e.bias + nc + d) : 0.f);
+                if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.qkv_vt)[base + (long long)d * e.qSpad] = __float2bfloat16_rn(o);
+                else reinterpret_cast<float*>(e.qkv_vt)[base + (long long)d * e.qSpad] = o;
+              }
+            }
+          }
+        } else if (vec_ok) {
           // 8 lanes cover one 128-byte row segment, 4 rows per instruction; all loads are issued before any store
           float4 res[8], v[8];
           if (e.residual) {
@@ -299,9 +353,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
   tc_fence_before();
@@ -337,8 +388,8 @@ int pick_bn(long long M, int N) {
   const long long mt = ceil_div<long long>(M, BM);
   int best = 64;
   double best_cost = 1e30;
-  const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
+  const int cands[2] = {128, 64};  // 256-wide tiles lose: the epilogue (not the operand traffic) bounds short-K GEMMs
+  for (int i = 0; i < 2; ++i) {
     const int bn = cands[i];
     const long long tiles = mt * ceil_div(N, bn);
     const double rounds = (double)ceil_div<long long>(tiles, sms);
@@ -376,6 +427,11 @@ int launch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiA
 
 }  // namespace
 
+namespace {
+struct QkvReq { void* q; void* k; void* vt; int S, Spad, H; };
+thread_local QkvReq g_qkv{nullptr, nullptr, nullptr, 0, 0, 0};
+}  // namespace
+
 extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
                                const float* bias, const float* residual, long long ldr, void* C, int c_dtype,
                                long long ldc, long long M, int N, int K, int act, int precision, cudaStream_t st) {
@@ -405,7 +461,10 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
     int rc = make_tensor_map(&tmB, W, w_dtype, 2, dims, str, box);
     if (rc) return rc;
   }
-  EpiArgs e{bias, residual, ldr, C, ldc, c_dtype == MMVID_DT_BF16, M, N, K, act, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  EpiArgs e{};
+  e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc; e.c_bf16 = c_dtype == MMVID_DT_BF16;
+  e.M = M; e.N = N; e.K = K; e.act = act;
+  if (g_qkv.q) { e.qkv_q = g_qkv.q; e.qkv_k = g_qkv.k; e.qkv_vt = g_qkv.vt; e.qS = g_qkv.S; e.qSpad = g_qkv.Spad; e.qH = g_qkv.H; }
   return tf32 ? launch_bn<true, false>(BN, tmA, tmB, e, st) : launch_bn<false, false>(BN, tmA, tmB, e, st);
 }
 
@@ -445,7 +504,26 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
     int rc = make_tensor_map(&tmB, p->w, MMVID_DT_F32, 2, dims, str, box);
     if (rc) return rc;
   }
-  EpiArgs e{p->bias, p->residual, (long long)p->Cout, p->out, (long long)p->Cout, 0, M, p->Cout, K, MMVID_ACT_NONE,
-            p->Cin, p->KW, p->pad_t, p->pad_l, BW, BH, BNI, p->W, p->H, 0, 0, 0};
+  EpiArgs e{};
+  e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_bf16 = 0;
+  e.M = M; e.N = p->Cout; e.K = K; e.act = MMVID_ACT_NONE;
+  e.cCin = p->Cin; e.cKW = p->KW; e.cPadT = p->pad_t; e.cPadL = p->pad_l; e.cBW = BW; e.cBH = BH; e.cBNI = BNI;
+  e.cW = p->W; e.cH = p->H;
   return launch_bn<true, true>(BN, tmA, tmB, e, st);
+}
+
+
+// Fused QKV projection: qkv = A W^T + b written directly as Q,K [B,H,S_pad,64] and V^T [B,H,64,S_pad]
+// (no [M, 3D] intermediate, no separate split/transposition pass).  Padding rows/columns are NOT touched:
+// the caller keeps the buffers zero-initialised.
+extern "C" int mmvid_linear_qkv(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
+                                const float* bias, void* q, void* k, void* vt, int out_dtype, int B, int H, int S,
+                                int S_pad, int precision, mmvid_stream_t stream) {
+  MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16, "tensor-core precision required");
+  MMVID_REQUIRE(S_pad >= S && S_pad % 64 == 0, "S_pad");
+  g_qkv = QkvReq{q, k, vt, S, S_pad, H};
+  const int rc = mmvid_linear_tc(A, a_dtype, lda, W, w_dtype, ldw, bias, nullptr, 0, q /*unused*/, out_dtype, 0,
+                                 (long long)B * S, 3 * H * 64, H * 64, MMVID_ACT_NONE, precision, to_stream(stream));
+  g_qkv = QkvReq{nullptr, nullptr, nullptr, 0, 0, 0};
+  return rc;
 }

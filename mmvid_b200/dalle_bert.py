@@ -311,9 +311,151 @@ class BERT(nn.Module):
             ops.embed_gather(control, self._control_segments(text, visual_ids))
         if not return_loss:
             return control
-        raise NotImplementedError(
-            "BERT.forward(return_loss=True) (training losses + backward kernels) is scheduled after the inference "
-            "path (SURVEY.md §8f rank 1); this build covers return_loss=False / generate_images.")
+        # ------------------------------------------------------------------ training losses (dalle_bert.py:980-1127)
+        if negvc:
+            raise NotImplementedError("negvc (explicit negative text/visual control) is not on the default training path")
+        target_orig = target
+        target_ids = self.get_image_tokens(target)
+        mask1, not_fully_masked = self._sample_msm_masks(B, dev, msm_strategy_prob, msm_bernoulli_prob, pc_prob)
+        target_warp_ids = None
+        if vid and self.num_targets > 1:
+            from .augment import warp
+            target_warp_ids = self.get_image_tokens(warp(target_orig, vid_strategy_prob))
+        return self._losses(text, visual_ids, target_ids, mask1, not_fully_masked, rel=rel, vid=vid,
+                            rel_no_fully_masked=rel_no_fully_masked, target_warp_ids=target_warp_ids)
+
+    # ------------------------------------------------------------------------------------------ training internals
+    def _sample_msm_masks(self, B, dev, strategy_prob, bernoulli_prob, pc_prob):
+        """Per-sample keep-masks for masked sequence modelling (dalle_bert.py:992-1029): True = ground truth kept.
+        Strategies: 1 bernoulli keep with p~U(a,b); 2 mask everything; 3 keep outside a random box; 4 keep inside it."""
+        import torchvision.transforms as T
+        if not hasattr(self, "random_erasing"):
+            self.random_erasing = T.RandomErasing(p=1, scale=(0.2, 0.8), ratio=(0.5, 2), value=0)
+        f, Tn, n = self.image_fmap_size, self.num_targets, self.image_seq_len
+        masks, nfm = [], torch.ones(B, device=dev)
+        for i in range(B):
+            strategy = int(np.random.choice([1, 2, 3, 4], p=strategy_prob))
+            if strategy == 1:
+                p = np.random.uniform(*bernoulli_prob)
+                m = torch.bernoulli(torch.ones(self.target_seq_len, device=dev) * p)
+            elif strategy == 2:
+                nfm[i] = 0
+                m = torch.zeros(self.target_seq_len, device=dev)
+            else:
+                box = self.random_erasing(torch.ones(Tn, 1, f, f, device=dev)).reshape(-1)
+                m = box if strategy == 3 else 1 - box
+            if pc_prob > 0 and random.random() < pc_prob:
+                for tt in random.sample(range(Tn), random.randint(1, Tn // 2)):
+                    m[n * tt:n * (tt + 1)] = 1
+            masks.append(m)
+        return torch.stack(masks, 0) == 1, nfm
+
+    def _embed_train(self, text, visual_ids, target_ids_masked):
+        """Residual stream [B,S,D] with autograd to every embedding table (same fused gather kernel as inference)."""
+        from .autograd import EmbedFn
+        B, dev, D = text.shape[0], text.device, self.dim
+
+        def seg(table, table2, pos, ids, pad=None):
+            n = ids.shape[1]
+            buf = torch.empty(B, n, D, device=dev, dtype=torch.float32)
+            return EmbedFn.apply(table, table2, pos, ids.contiguous(), B, n, 0, pad, buf)
+
+        parts = [seg(self.special_emb.weight, self.special_pos_emb.weight, None, self._const_ids([0], dev).expand(B, 1).contiguous()),
+                 seg(self.text_emb.weight, None, self.text_pos_emb.weight, text, (0, self.num_text_tokens - self.text_seq_len))]
+        if self.num_visuals > 0:
+            table = self.visual_emb.weight if self.visual_emb is not None else self.image_emb.weight
+            parts.append(seg(table, None, self._axial_pos(self.visual_pos_emb), visual_ids))
+        parts.append(seg(self.special_emb.weight, self.special_pos_emb.weight, None,
+                         self._const_ids([1, 2], dev).expand(B, 2).contiguous()))
+        control = torch.cat(parts, dim=1)
+        target = seg(self.image_emb.weight, None, self._axial_pos(self.target_pos_emb), target_ids_masked)
+        return control, target
+
+    @staticmethod
+    def _axial_pos(mod):
+        """Differentiable [n, D] position table (sum of broadcast axis tables) for the training path."""
+        mods = list(mod.module_list) if hasattr(mod, "module_list") else [mod]
+        tabs = []
+        for m in mods:
+            ws = m.axis_weights()
+            t = ws[0]
+            for w in ws[1:]:
+                t = t + w
+            tabs.append(t.reshape(-1, m.dim))
+        return torch.cat(tabs, 0) if len(tabs) > 1 else tabs[0]
+
+    def _transformer_train(self, tokens):
+        from .autograd import AttentionFn, LayerNormFn, LinearFn
+        from ._lib import ACT_NONE, ACT_QUICKGELU, BF16
+        tr = self.transformer
+        prec = PRECISIONS[tr.precision]
+        if prec == BF16:
+            prec = 1  # training runs the tf32 tensor-core path (bf16 activations are an inference-only mode)
+        B, S, D = tokens.shape
+        H = tr.transformer.heads
+        x = tokens.reshape(B * S, D)
+        for blk in tr.transformer.resblocks:
+            h = LayerNormFn.apply(x, blk.ln_1.weight, blk.ln_1.bias, 1e-5)
+            qkv = LinearFn.apply(h, blk.attn.in_proj_weight, blk.attn.in_proj_bias, ACT_NONE, prec)
+            att = AttentionFn.apply(qkv, B, S, H, tr.mask_kind, tr.mask_rows, prec)
+            x = x + LinearFn.apply(att, blk.attn.out_proj.weight, blk.attn.out_proj.bias, ACT_NONE, prec)
+            h = LayerNormFn.apply(x, blk.ln_2.weight, blk.ln_2.bias, 1e-5)
+            h = LinearFn.apply(h, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, ACT_QUICKGELU, prec)
+            x = x + LinearFn.apply(h, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, ACT_NONE, prec)
+        return x.view(B, S, D)
+
+    def _head_train(self, rows, seq):
+        from .autograd import LayerNormFn, LinearFn
+        from ._lib import ACT_NONE, FP32
+        h = LayerNormFn.apply(rows, seq[0].weight, seq[0].bias, 1e-5)
+        prec = PRECISIONS[self.transformer.precision]
+        if prec == 2:
+            prec = 1                      # bf16 is inference-only; training GEMMs run tf32
+        if seq[1].weight.shape[0] < 8:
+            prec = FP32                   # scalar REL / VID heads: CUDA-core path
+        return LinearFn.apply(h, seq[1].weight, seq[1].bias, ACT_NONE, prec)
+
+    def _losses(self, text, visual_ids, target_ids, mask1, not_fully_masked, rel=False, vid=False,
+                rel_no_fully_masked=False, target_warp_ids=None, swap_perm=None):
+        """MSM / REL / VID losses (dalle_bert.py:1030-1127) for given masks; autograd flows to all trainable params."""
+        from .autograd import cross_entropy_selected
+        B, dev, D = text.shape[0], text.device, self.dim
+        MASK = self.image_token_lut["[MASK]"]
+        csl, Ttot = self.control_seq_len, self.target_seq_len
+        tgt_masked = torch.where(mask1, target_ids, torch.full_like(target_ids, MASK))
+        control, target_emb = self._embed_train(text, visual_ids, tgt_masked)
+        out = self._transformer_train(torch.cat((control, target_emb), dim=1))
+        logits = self._head_train(out[:, csl:].reshape(B * Ttot, D), self.to_logits)
+        loss_msm = cross_entropy_selected(logits, target_ids.reshape(-1), (~mask1).reshape(-1))
+        bce = F.binary_cross_entropy_with_logits
+        ones, zeros = torch.ones(B, device=dev), torch.zeros(B, device=dev)
+        denom = max(1.0, float(not_fully_masked.sum()))
+        if rel:
+            assert B >= 2 and B % 2 == 0, "REL needs an even batch (control sequences are swapped between halves)"
+            perm = swap_perm if swap_perm is not None else torch.cat((torch.arange(B // 2, B), torch.arange(0, B // 2))).to(dev)
+            out_neg = self._transformer_train(torch.cat((control[perm], target_emb), dim=1))
+            lp = self._head_train(out[:, self.rel_tok_index], self.to_logits_rel).squeeze(-1)
+            ln = self._head_train(out_neg[:, self.rel_tok_index], self.to_logits_rel).squeeze(-1)
+            if rel_no_fully_masked:
+                loss_rel = ((bce(lp, ones, reduction="none") + bce(ln, zeros, reduction="none")) * not_fully_masked).sum() / denom
+            else:
+                loss_rel = bce(lp, ones) + bce(ln, zeros)
+        else:
+            loss_rel = torch.tensor(0.0, device=dev)
+        if vid and self.num_targets > 1:
+            warp_masked = torch.where(mask1, target_warp_ids, torch.full_like(target_warp_ids, MASK))
+            _, warp_emb = self._embed_train(text, visual_ids, warp_masked)
+            out_neg = self._transformer_train(torch.cat((control, warp_emb), dim=1))
+            lp = self._head_train(out[:, self.vid_tok_index], self.to_logits_vid)
+            ln = self._head_train(out_neg[:, self.vid_tok_index], self.to_logits_vid)
+            o1, z1 = torch.ones(B, 1, device=dev), torch.zeros(B, 1, device=dev)
+            if rel_no_fully_masked:
+                loss_vid = bce(lp, o1, reduction="none").sum() / denom + bce(ln, z1, reduction="none").sum() / denom
+            else:
+                loss_vid = bce(lp, o1) + bce(ln, z1)
+        else:
+            loss_vid = torch.tensor(0.0, device=dev)
+        return loss_msm, loss_rel, loss_vid
 
     def _visual_eraser(self):
         import torchvision.transforms as T

@@ -219,6 +219,41 @@ def attention_tc(qkv, B, S, H, mask_kind, prev_rows_host, precision, out_dtype=t
     return out
 
 
+def alloc_qkv_buffers(B, H, S, precision, device):
+    """Zero-initialised Q,K [B,H,S_pad,64] and V^T [B,H,64,S_pad] (padding must stay zero: P x garbage = NaN)."""
+    precision = precision_id(precision)
+    S_pad = (S + 127) // 128 * 128
+    dt = torch.float32 if precision == TF32 else torch.bfloat16
+    q = torch.zeros(B, H, S_pad, 64, device=device, dtype=dt)
+    k = torch.zeros(B, H, S_pad, 64, device=device, dtype=dt)
+    vt = torch.zeros(B, H, 64, S_pad, device=device, dtype=dt)
+    return q, k, vt
+
+
+def linear_qkv(a, w, bias, bufs, B, S, H, precision):
+    """Fused in-projection: writes Q,K,V^T of `a @ w.T + bias` straight into the attention layout."""
+    lib = L.load()
+    precision = precision_id(precision)
+    q, k, vt = bufs
+    S_pad = q.shape[2]
+    a2 = a.reshape(B * S, H * 64)
+    assert a2.stride(1) == 1 and w.stride(1) == 1 and w.shape == (3 * H * 64, H * 64)
+    L.check(lib.mmvid_linear_qkv(_ptr(a2), _dt(a2), a2.stride(0), _ptr(w), _dt(w), w.stride(0), _ptr(bias), _ptr(q), _ptr(k),
+                                 _ptr(vt), _dt(q), B, H, S, S_pad, precision, _stream()), "linear_qkv")
+
+
+def attention_core(bufs, B, S, H, mask_kind, prev_rows_host, precision, out_dtype=torch.float32):
+    lib = L.load()
+    precision = precision_id(precision)
+    q, k, vt = bufs
+    S_pad = q.shape[2]
+    out = torch.empty(B * S, H * 64, device=q.device, dtype=out_dtype)
+    pr = (C.c_int * 4)(*(list(prev_rows_host) + [0] * (4 - len(prev_rows_host))))
+    L.check(lib.mmvid_attention(_ptr(q), _ptr(k), _ptr(vt), _ptr(out), _dt(out), out.stride(0), B, H, S, S_pad,
+                                mask_kind, pr, len(prev_rows_host), precision, _stream()), "attention")
+    return out
+
+
 def kv_append(qkv, kcache, vcache, pos):
     lib = L.load()
     B, H, S_max, _ = kcache.shape

@@ -108,6 +108,13 @@ class OpenAICLIPTransformer(nn.Module):
             self._rows_dev = torch.tensor(list(self.mask_rows) or [0], dtype=torch.int32, device=device)
         return self._rows_dev
 
+    def _qkv_buffers(self, B, S, H, prec, device):
+        key = (B, S, H, prec, str(device))
+        if getattr(self, "_qkv_key", None) != key:
+            self._qkv_bufs = ops.alloc_qkv_buffers(B, H, S, prec, device)
+            self._qkv_key = key
+        return self._qkv_bufs
+
     def _w(self, p, prec):
         return self._bf16.get(p) if prec == BF16 else p.detach()
 
@@ -123,15 +130,21 @@ class OpenAICLIPTransformer(nn.Module):
         first = True
         for li, blk in enumerate(self.transformer.resblocks):
             h = ops.layernorm(x, blk.ln_1.weight, blk.ln_1.bias, 1e-5, out_dtype=act_dt)
-            qkv = ops.linear(h, self._w(blk.attn.in_proj_weight, prec), blk.attn.in_proj_bias, precision=prec)
-            if kv_out is not None:  # prefill of the ART-V K/V cache: [B,H,S_max,64] per layer
-                kv = qkv.view(B, S, 3, H, 64)
-                kv_out[0][li][:, :, :S].copy_(kv[:, :, 1].permute(0, 2, 1, 3))
-                kv_out[1][li][:, :, :S].copy_(kv[:, :, 2].permute(0, 2, 1, 3))
             if prec == FP32:
+                qkv = ops.linear(h, self._w(blk.attn.in_proj_weight, prec), blk.attn.in_proj_bias, precision=prec)
+                if kv_out is not None:  # prefill of the ART-V K/V cache: [B,H,S_max,64] per layer
+                    kv = qkv.view(B, S, 3, H, 64)
+                    kv_out[0][li][:, :, :S].copy_(kv[:, :, 1].permute(0, 2, 1, 3))
+                    kv_out[1][li][:, :, :S].copy_(kv[:, :, 2].permute(0, 2, 1, 3))
                 att = ops.attention_fp32(qkv, B, S, H, self.mask_kind, self._prev_rows_dev(x.device))
             else:
-                att = ops.attention_tc(qkv, B, S, H, self.mask_kind, self.mask_rows, prec, out_dtype=act_dt)
+                # in-projection GEMM whose epilogue scatters Q, K and V^T straight into the attention layout
+                bufs = self._qkv_buffers(B, S, H, prec, x.device)
+                ops.linear_qkv(h, self._w(blk.attn.in_proj_weight, prec), blk.attn.in_proj_bias, bufs, B, S, H, prec)
+                if kv_out is not None:
+                    kv_out[0][li][:, :, :S].copy_(bufs[1][:, :, :S])
+                    kv_out[1][li][:, :, :S].copy_(bufs[2][:, :, :, :S].transpose(2, 3))
+                att = ops.attention_core(bufs, B, S, H, self.mask_kind, self.mask_rows, prec, out_dtype=act_dt)
             out = torch.empty_like(x) if first else x  # never write into the caller's tensor
             first = False
             x = ops.linear(att, self._w(blk.attn.out_proj.weight, prec), blk.attn.out_proj.bias, residual=x,

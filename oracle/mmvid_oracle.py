@@ -557,3 +557,57 @@ def artv_generate_tokens(spec, sd, text, visual_tokens=None, filter_thres=0.5, t
         sample = sample - spec.num_control_tokens  # is_image is always true here (:259, :278)
         out = torch.cat((out, sample), dim=-1)
     return out[:, spec.text_seq_len:]
+
+
+# ------------------------------------------------------------------------------------------------
+# BERT training losses  (mmvid_pytorch/dalle_bert.py:1030-1127) for GIVEN masks / negatives, so that the RNG-driven
+# mask sampling (:992-1029) and frame warping (:204-238) stay outside the checked arithmetic.
+# ------------------------------------------------------------------------------------------------
+
+
+def bert_train_losses(spec, sd, text, visual_tokens, target_tokens, mask1, not_fully_masked, rel=False, vid=False,
+                      rel_no_fully_masked=False, target_warp_tokens=None):
+    """Returns (loss_msm, loss_rel, loss_vid); differentiable w.r.t. the tensors in `sd` that require grad.
+    mask1: bool [B, T*n], True = ground-truth token kept (dalle_bert.py:1029-1031)."""
+    B = text.shape[0]
+    dev = text.device
+    control = bert_control_emb(spec, sd, text, visual_tokens)
+    csl = control.shape[1]
+    attn_mask = spec.attn_mask().to(dev)
+    pos = bert_target_pos_emb(spec, sd, 1)
+
+    def fwd(c, tokens):
+        emb = F.embedding(tokens, sd["image_emb.weight"]) + pos
+        return transformer_forward(torch.cat((c, emb), dim=1), sd, "transformer.transformer.", attn_mask)
+
+    tgt_masked = torch.where(mask1, target_tokens, torch.full_like(target_tokens, spec.MASK))
+    out = fwd(control, tgt_masked)
+    logits = _to_logits(out[:, csl:], sd, "to_logits.")
+    loss_msm = F.cross_entropy(logits[~mask1], target_tokens[~mask1])  # :1040
+    bce = F.binary_cross_entropy_with_logits
+    denom = max(1.0, float(not_fully_masked.sum()))
+    if rel:
+        swapped = torch.cat(torch.chunk(control, 2, dim=0)[::-1], dim=0)  # swap() for an even batch (:110-113)
+        out_neg = fwd(swapped, tgt_masked)
+        lp = _to_logits(out[:, spec.rel_tok_index], sd, "to_logits_rel.").squeeze()
+        ln = _to_logits(out_neg[:, spec.rel_tok_index], sd, "to_logits_rel.").squeeze()
+        if rel_no_fully_masked:
+            loss_rel = (bce(lp, torch.ones(B, device=dev), reduction="none") * not_fully_masked +
+                        bce(ln, torch.zeros(B, device=dev), reduction="none") * not_fully_masked).sum() / denom
+        else:
+            loss_rel = bce(lp, torch.ones(B, device=dev)) + bce(ln, torch.zeros(B, device=dev))
+    else:
+        loss_rel = torch.tensor(0.0, device=dev)
+    if vid and spec.num_targets > 1:
+        warp_masked = torch.where(mask1, target_warp_tokens, torch.full_like(target_warp_tokens, spec.MASK))
+        out_neg = fwd(control, warp_masked)
+        lp = _to_logits(out[:, spec.vid_tok_index], sd, "to_logits_vid.")
+        ln = _to_logits(out_neg[:, spec.vid_tok_index], sd, "to_logits_vid.")
+        if rel_no_fully_masked:
+            loss_vid = bce(lp, torch.ones(B, 1, device=dev), reduction="none").sum() / denom + \
+                bce(ln, torch.zeros(B, 1, device=dev), reduction="none").sum() / denom
+        else:
+            loss_vid = bce(lp, torch.ones(B, 1, device=dev)) + bce(ln, torch.zeros(B, 1, device=dev))
+    else:
+        loss_vid = torch.tensor(0.0, device=dev)
+    return loss_msm, loss_rel, loss_vid

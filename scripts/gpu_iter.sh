@@ -6,7 +6,7 @@ run() { local name=$1; shift; local to=$1; shift
   echo "=== $name" | tee -a $S
   timeout $to python -m pytest "$@" -m gpu -q -s -p no:cacheprovider > gpurun_out/$name.log 2>&1
   echo "exit $?" | tee -a $S; tail -n 4 gpurun_out/$name.log | tee -a $S; }
-run it_k_lin 300 tests/test_gpu_kernels.py -k "linear or conv3x3_tensor_core or conv_out_fused or groupnorm"
+run it_k_lin 300 tests/test_gpu_kernels.py -k "linear or conv3x3_tensor_core or conv_out_fused or groupnorm or fused_qkv"
 run it_k_att 300 tests/test_gpu_kernels.py -k "attention and (tf32 or bf16)"
 run it_models 1200 tests/test_gpu_models.py -k "tf32 or bf16 or batched or tensor_core or vae"
 for prec in tf32 bf16; do

@@ -148,6 +148,54 @@ def test_attention_masks(prec, B, S, H, kind):
     assert e < TOL[prec], f"{prec} {kind} S={S}: {e}"
 
 
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("kind", ["prev", "causal"])
+def test_attention_large_score_range_exercises_lazy_rescale(prec, kind):
+    """Scores with a wide dynamic range force the running-max reference to move many times (the O *= alpha path
+    of the lazy-rescale schedule); growing key magnitude along the sequence makes later tiles dominate."""
+    ops = _ops()
+    from oracle import mmvid_oracle as O
+    B, S, H = 1, 700, 2
+    g = torch.Generator().manual_seed(99)
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g)
+    ramp = torch.linspace(0.5, 4.0, S).repeat(B).unsqueeze(1)
+    qkv[:, H * 64:2 * H * 64] *= ramp          # keys grow along the sequence -> max keeps increasing tile after tile
+    qkv[:, :H * 64] *= 2.0
+    qkv = qkv.cuda()
+    if kind == "prev":
+        mask, mk, pr = O.build_attention_mask(S, "mask_prev", (100, 101)), ops.MASK_PREV, (100, 101)
+    else:
+        mask, mk, pr = O.build_attention_mask(S, "causal"), ops.MASK_CAUSAL, ()
+    ref = _attn_ref(qkv, B, S, H, mask)
+    out = ops.attention_tc(qkv, B, S, H, mk, pr, prec, out_dtype=torch.bfloat16 if prec == "bf16" else torch.float32).float()
+    e = relerr(out, ref)
+    assert e < (3e-3 if prec == "tf32" else 3e-2), f"{prec} {kind}: {e}"
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("B,S,H", [(2, 37, 2), (1, 565, 12), (3, 128, 4)])
+def test_fused_qkv_projection_scatter_matches_split(prec, B, S, H):
+    """mmvid_linear_qkv (GEMM epilogue writes Q,K,V^T in attention layout) vs linear + qkv_split."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 100 + S)
+    D = H * 64
+    x = torch.randn(B * S, D, generator=g).cuda()
+    w = (torch.randn(3 * D, D, generator=g) / math.sqrt(D)).cuda()
+    b = torch.randn(3 * D, generator=g).cuda()
+    ref = F.linear(x.double(), w.double(), b.double()).float().view(B, S, 3, H, 64)
+    bufs = ops.alloc_qkv_buffers(B, H, S, prec, "cuda")
+    if prec == "bf16":
+        ops.linear_qkv(x.bfloat16(), w.bfloat16(), b, bufs, B, S, H, prec)
+    else:
+        ops.linear_qkv(x, w, b, bufs, B, S, H, prec)
+    q, k, vt = [t.float() for t in bufs]
+    tol = TOL[prec]
+    assert relerr(q[:, :, :S], ref[:, :, 0].permute(0, 2, 1, 3)) < tol
+    assert relerr(k[:, :, :S], ref[:, :, 1].permute(0, 2, 1, 3)) < tol
+    assert relerr(vt[:, :, :, :S], ref[:, :, 2].permute(0, 2, 3, 1)) < tol
+    assert float(q[:, :, S:].abs().max() if q.shape[2] > S else 0) == 0 and float(vt[:, :, :, S:].abs().max() if vt.shape[3] > S else 0) == 0
+
+
 def test_vq_argmin_bit_exact_and_ties():
     ops = _ops()
     from oracle import mmvid_oracle as O

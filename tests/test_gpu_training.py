@@ -1,0 +1,94 @@
+"""GPU: BERT.forward(return_loss=True) - loss values and parameter gradients of the CUDA training path against
+the oracle's torch-autograd restatement of dalle_bert.py:1030-1127 on the same weights, masks and negatives."""
+import numpy as np
+import pytest
+import torch
+
+from cases import BERT_CASES
+from helpers import bert_spec, build_bert, relerr, to_device
+from mmvid_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference_math():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+@pytest.mark.parametrize("prec,tol_loss,tol_grad", [("fp32", 2e-5, 2e-4), ("tf32", 2e-3, 2e-2)])
+@pytest.mark.parametrize("name", ["bert_tiny", "bert_tiny_nov"])
+def test_training_losses_and_gradients_match_oracle_autograd(name, prec, tol_loss, tol_grad):
+    from oracle import mmvid_oracle as O
+    cfg = BERT_CASES[name]
+    model, sd = build_bert(cfg, precision=prec)
+    model.train()
+    spec = bert_spec(cfg)
+    B = cfg["batch"]
+    g = torch.Generator().manual_seed(3)
+    text = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], cfg["seed"]).cuda()
+    vis_ids = torch.randint(0, 1024, (B, spec.visual_seq_len), generator=g).cuda() if cfg["num_visuals"] > 0 else None
+    tgt = torch.randint(0, 1024, (B, spec.target_seq_len), generator=g).cuda()
+    warp = torch.randint(0, 1024, (B, spec.target_seq_len), generator=g).cuda()
+    mask1 = (torch.rand(B, spec.target_seq_len, generator=g) < 0.4).cuda()
+    mask1[0, :2] = False
+    nfm = torch.ones(B).cuda()
+    # oracle (torch autograd, fp32, same GPU)
+    sd_o = {k: v.clone().cuda().requires_grad_(v.is_floating_point() and not k.startswith(("vae.", "cvae.")))
+            for k, v in sd.items()}
+    lo = O.bert_train_losses(spec, sd_o, text, vis_ids, tgt, mask1, nfm, rel=True, vid=True, target_warp_tokens=warp)
+    (7 * lo[0] + 0.5 * lo[1] + 0.5 * lo[2]).backward()   # train.py:320 weighting (utils_args.py:399-410)
+    lm = model._losses(text, vis_ids, tgt, mask1, nfm, rel=True, vid=True, target_warp_ids=warp)
+    (7 * lm[0] + 0.5 * lm[1] + 0.5 * lm[2]).backward()
+    for a, b, nm in zip(lm, lo, ("msm", "rel", "vid")):
+        e = abs(float(a) - float(b)) / max(abs(float(b)), 1e-6)
+        print(f"{name} {prec} loss_{nm}: {float(a):.6f} vs oracle {float(b):.6f} (rel {e:.2e})")
+        assert e < tol_loss
+    checked = 0
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        go = sd_o[k].grad
+        assert p.grad is not None, f"no gradient for {k}"
+        if go is None or float(go.norm()) == 0:
+            continue
+        e = relerr(p.grad, go)
+        worst = max(worst, e)
+        assert e < tol_grad, f"{k}: grad relerr {e:.3e}"
+        checked += 1
+    print(f"{name} {prec}: {checked} parameter gradients checked, worst relerr {worst:.2e}")
+    assert checked > 20
+
+
+def test_reference_train_call_signature_and_optimizer_step():
+    """The call train.py:298-325 makes: losses -> weighted sum -> backward -> clip -> Adam step; loss must go down."""
+    cfg = BERT_CASES["bert_tiny"]
+    model, _ = build_bert(cfg, precision="tf32")
+    model.train()
+    B = 4
+    np.random.seed(0)
+    torch.manual_seed(0)
+    import random
+    random.seed(0)
+    text = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], 1).cuda()
+    visual = synth.synth_frames(B, cfg["num_visuals"], cfg["image_size"], 2).cuda()
+    frames = synth.synth_frames(B, cfg["num_targets"], cfg["image_size"], 3).cuda()
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=3e-3)
+    hist = []
+    for it in range(6):
+        np.random.seed(1)
+        random.seed(1)
+        torch.manual_seed(1)  # same masks every iteration so the loss is comparable
+        loss_msm, loss_rel, loss_vid = model(text, visual=visual, target=frames, return_loss=True, rel=True, vid=True,
+                                             msm_strategy_prob=np.array([0.7, 0.1, 0.1, 0.1]),
+                                             msm_bernoulli_prob=[0.2, 0.5], vid_strategy_prob=np.array([0.25] * 4))
+        loss = 7 * loss_msm + 0.5 * loss_rel + 0.5 * loss_vid
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        hist.append(float(loss))
+    print("training loss history:", [round(h, 4) for h in hist])
+    assert all(np.isfinite(hist)) and hist[-1] < hist[0]
