@@ -346,8 +346,15 @@ def run_ours(args):
         kr = kernel_roofline(model, args, peaks, S, B)
         dom = "attention" if "attention" in kr else "gemm_c_fc"
         peak = peaks["bf16_tflops"]
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if dom == "attention" and args.precision == "tf32" and args.shape == "A" and B == 4:
+                traffic = tj["attention_tc2_kernel_tf32_shapeA_b4"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         roof = {"bound": "tensor", "kernel": dom, "achieved": kr[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": kr[dom]["tflops"] / peak, "traffic": None, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
+                "frac": kr[dom]["tflops"] / peak, "traffic": traffic, "peak_source": peaks["source"] + " cuBLAS bf16 burst",
                 "note": "kind::tf32 issues at half the kind::f16 rate; frac_of_half_rate = achieved / (peak/2)"
                         if args.precision == "tf32" else "",
                 "frac_of_half_rate": kr[dom]["tflops"] / (peak / 2) if args.precision == "tf32" else None,

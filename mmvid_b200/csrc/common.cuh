@@ -83,4 +83,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// tensor-core epilogues (tf32 / bf16 modes): sigmoid through MUFU ex2 + rcp (~1e-6 relative, far inside the mode's
+// own rounding) instead of the ~40-instruction accurate expf + IEEE division
+__device__ __forceinline__ float apply_act_fast(float v, int act) {
+  if (act == MMVID_ACT_NONE) return v;
+  const float k = act == MMVID_ACT_QUICKGELU ? -1.702f * 1.4426950408889634f : -1.4426950408889634f;
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(k * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return v * r;
+}
+
 }  // namespace mmvid

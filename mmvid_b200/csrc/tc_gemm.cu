@@ -61,7 +61,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_LD = 36;  // floats per staged row (32 + 4 pad: conflict-free 128-bit writes and reads)
+constexpr int EPI_LD = 32;  // floats per staged row; 16-byte units are XOR-swizzled with the row index (no padding)
 
 struct EpiArgs {
   const float* bias;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void tile_coords(const EpiArgs& e, int tile, int& mt,
 }
 
 template <int BN>
-constexpr int gemm_stages() { return BN == 256 ? 3 : (BN == 128 ? 5 : 7); }
+constexpr int gemm_stages() { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
 
 template <int BN>
 constexpr size_t gemm_smem_bytes() {
@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
     const uint32_t st_wr = st_base + (uint32_t)(lane * EPI_LD * 4);                       // my row while transposing
     const int col = (lane & 7) * 4, rsub = lane >> 3;                                     // coalesced phase mapping
-    const uint32_t st_rd = st_base + (uint32_t)((rsub * EPI_LD + col) * 4);
+    // row r keeps its 16-byte unit u at physical unit (u ^ (r & 7)): conflict-free 128-bit writes (one row per lane)
+    // and reads (8 lanes per row) without padding.  Reader rows are rsub + 4*i, so (row & 7) = (rsub + 4*i) & 7.
+    const uint32_t st_rd_row = st_base + (uint32_t)(rsub * EPI_LD * 4);
     const bool vec_ok = (e.N % 4 == 0) && (e.ldc % 4 == 0) && (!e.residual || e.ldr % 4 == 0);
     constexpr int NCH = BN / 64;          // chunks per warp (half of the tile's BN/32)
     uint32_t tile_iter = 0;
@@ -255,8 +257,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         uint32_t (&r)[32] = racc[c];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          sts128(st_wr + j * 16, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                 __uint_as_float(r[4 * j + 3]));
+          sts128(st_wr + (uint32_t)(((j ^ (lane & 7)) * 16)), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         __syncwarp();
         const int n = n0 + c * 32 + col;
         const bool n_ok = n < e.N;
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             for (int i = 0; i < 8; ++i) {
               const long long m = m_first + i * 4;
               if (m >= e.M) continue;
-              const float4 v = lds128(st_rd + (uint32_t)(i * 4 * EPI_LD * 4));
+              const float4 v = lds128(st_rd_row + (uint32_t)(i * 4 * EPI_LD * 4) + (uint32_t)((((lane & 7) ^ ((rsub + 4 * i) & 7)) * 16)));
               const int bb = (int)(m / e.qS), ss = (int)(m - (long long)bb * e.qS);
               const long long off = (((long long)bb * e.qH + hh) * e.qSpad + ss) * 64 + d0 + col;
               const float o0 = v.x + bias_r[c].x, o1 = v.y + bias_r[c].y, o2 = v.z + bias_r[c].z, o3 = v.w + bias_r[c].w;
@@ -312,14 +314,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = lds128(st_rd + (uint32_t)(i * 4 * EPI_LD * 4));
+          for (int i = 0; i < 8; ++i) v[i] = lds128(st_rd_row + (uint32_t)(i * 4 * EPI_LD * 4) + (uint32_t)((((lane & 7) ^ ((rsub + 4 * i) & 7)) * 16)));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const long long m = m_first + i * 4;
             float o[4] = {v[i].x + bias_r[c].x, v[i].y + bias_r[c].y, v[i].z + bias_r[c].z, v[i].w + bias_r[c].w};
             if (e.act != MMVID_ACT_NONE) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], e.act);
+              for (int j = 0; j < 4; ++j) o[j] = apply_act_fast(o[j], e.act);
             }
             if (e.residual) { o[0] += res[i].x; o[1] += res[i].y; o[2] += res[i].z; o[3] += res[i].w; }
             if (m < e.M && n_ok) {
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int i = 0; i < 8; ++i) {
             const long long m = m_first + i * 4;
             if (m >= e.M || !n_ok) continue;
-            const float4 v = lds128(st_rd + (uint32_t)(i * 4 * EPI_LD * 4));
+            const float4 v = lds128(st_rd_row + (uint32_t)(i * 4 * EPI_LD * 4) + (uint32_t)((((lane & 7) ^ ((rsub + 4 * i) & 7)) * 16)));
             const float o[4] = {v.x + bias_r[c].x, v.y + bias_r[c].y, v.z + bias_r[c].z, v.w + bias_r[c].w};
             for (int j = 0; j < 4; ++j) {
               if (n + j >= e.N) break;
@@ -411,7 +413,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream
   }
   e.num_m_tiles = (int)ceil_div<long long>(e.M, BM);
   e.num_n_tiles = ceil_div(e.N, BN);
-  e.raster = env_int("MMVID_GEMM_RASTER", 0);
+  e.raster = env_int("MMVID_GEMM_RASTER", 1);  // n fastest: consecutive CTAs share the activation tile (measured best)
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   gemm_tc_kernel<TF32, BN, CONV><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, e);

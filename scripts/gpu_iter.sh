@@ -9,6 +9,7 @@ run() { local name=$1; shift; local to=$1; shift
 run it_k_lin 300 tests/test_gpu_kernels.py -k "linear or conv3x3_tensor_core or conv_out_fused or groupnorm or fused_qkv"
 run it_k_att 300 tests/test_gpu_kernels.py -k "attention and (tf32 or bf16)"
 run it_models 1200 tests/test_gpu_models.py -k "tf32 or bf16 or batched or tensor_core or vae"
+run it_train 900 tests/test_gpu_training.py
 for prec in tf32 bf16; do
   echo "=== bench $prec" | tee -a $S
   timeout 600 python bench.py --steps 3 --warmup 3 --precision $prec --no-cpu-baseline > gpurun_out/it_bench_$prec.json 2> gpurun_out/it_bench_$prec.err; echo "exit $?" | tee -a $S

@@ -11,10 +11,11 @@ from mmvid_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True)
-def _fp32_reference_math():
+@pytest.fixture(autouse=True)
+def _fp32_reference_math_with_grad():
     torch.backends.cuda.matmul.allow_tf32 = False
-    yield
+    with torch.enable_grad():
+        yield
 
 
 @pytest.mark.parametrize("prec,tol_loss,tol_grad", [("fp32", 2e-5, 2e-4), ("tf32", 2e-3, 2e-2)])
