@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--mp-steps", type=int, default=20)
     ap.add_argument("--vae-precision", default=None, choices=["tf32", "fp32"],
                     help="VQGAN conv precision (default: tf32 tensor cores unless --precision fp32)")
+    ap.add_argument("--workload", default="bert", choices=["bert", "artv"],
+                    help="bert: BERT mask-predict generate_images (headline); artv: ART-V KV-cache autoregressive generate_images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="ncu mode: no warm-up, one step, no side measurements")
     return ap.parse_args()
@@ -191,7 +193,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def build_artv(args, device):
+    from mmvid_b200.dalle_artv import DALLE
+    from mmvid_b200.vae import VQGanVAE1024
+    cfg = SHAPES[args.shape]
+    torch.manual_seed(1234)
+    vprec = args.vae_precision or ("fp32" if args.precision == "fp32" else "tf32")
+    vae = VQGanVAE1024(vae_path=None, image_size=cfg["image_size"], precision=vprec)
+    vae.image_size = cfg["image_size"]
+    vae.model.quantize.embedding.weight.data.normal_(0, 0.3)
+    model = DALLE(dim=DIM, vae=vae, cvae=vae, num_text_tokens=VOCAB, text_seq_len=cfg["text_seq_len"],
+                  which_transformer="openai_clip_visual", num_visuals=1, num_targets=cfg["num_targets"],
+                  openai_clip_path=None, transformer_layers=LAYERS, precision=args.precision, sampling_mode="batched")
+    return model.to(device).eval()
+
+
 def build_model(args, device):
+    if args.workload == "artv":
+        return build_artv(args, device)
     from mmvid_b200.dalle_bert import BERT
     from mmvid_b200.vae import VQGanVAE1024
     cfg = SHAPES[args.shape]
@@ -294,12 +313,19 @@ def run_ours(args):
     flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
     torch.manual_seed(42 + rank)  # train.py:87 seeds seed+rank the same way
 
+    artv_visual = None
+    if args.workload == "artv":
+        artv_visual = torch.rand(B, 1, 3, cfg["image_size"], cfg["image_size"], generator=g).to(dev)
+
     def step(e2e):
         if e2e:
             text = host_text.to(dev, non_blocking=True)
         else:
             text = dev_text
-        images, _, seq = model.generate_images(text, mask_predict_steps=args.mp_steps, dynamic=False)
+        if args.workload == "artv":
+            images, _, seq = model.generate_images(text, visual=artv_visual)
+        else:
+            images, _, seq = model.generate_images(text, mask_predict_steps=args.mp_steps, dynamic=False)
         if world > 1:
             images = all_gather_variable(images.contiguous(), [B] * world)
         if e2e:
@@ -343,7 +369,7 @@ def run_ours(args):
     value, e2e_value = total_tokens / t_dev, total_tokens / t_e2e
     if rank == 0:
         S = 1 + cfg["text_seq_len"] + 2 + tokens_per_sample
-        kr = kernel_roofline(model, args, peaks, S, B)
+        kr = kernel_roofline(model, args, peaks, S, B) if args.workload == "bert" else {"gemm_c_fc": dict(ms=0.0, tflops=0.0)}
         dom = "attention" if "attention" in kr else "gemm_c_fc"
         peak = peaks["bf16_tflops"]
         traffic = None
@@ -364,7 +390,8 @@ def run_ours(args):
             "value": value, "unit": "video-tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"tf32": "tf32 (fp32 storage, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
-            "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
+            "data": "synthetic", "config": dict(workload_config(args, B), **({"workload": "DALLE(ART-V).generate_images with KV cache, shape " + args.shape + ": prefix 1+L+n, " + str(tokens_per_sample) + " decode steps, batch " + str(B)} if args.workload == "artv" else {})),
+            "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "video-tokens/s", "h2d_bytes_per_step": host_text.numel() * 8,
                     "d2h_bytes_per_step": host_frames.numel() * 4, "ms_per_step": 1000.0 * t_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof,

@@ -126,6 +126,16 @@ int mmvid_linear_small_m(const float* A, long long lda, const float* W, long lon
 int mmvid_kv_append(const float* qkv, long long qkv_bstride, float* kcache, float* vcache, int B, int H, int S_max,
                     int pos, mmvid_stream_t stream);
 
+/* One full decode step (all layers, B <= 16 new tokens) issued natively: h [B,D] updated in place.
+ * ws: caller workspace of mmvid_artv_decode_workspace_floats(B, D, H) floats. */
+typedef struct {
+  const float *ln1_w, *ln1_b, *in_w, *in_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
+  float *kcache, *vcache; /* [B, H, S_max, 64] */
+} mmvid_decode_layer;
+long long mmvid_artv_decode_workspace_floats(int B, int D, int H);
+int mmvid_artv_decode_step(const mmvid_decode_layer* host_layers, int n_layers, float* h, float* ws, int B, int D, int H,
+                           int S_max, int pos, mmvid_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K14  VQ nearest-codeword lookup (taming/modules/vqvae/quantize.py:302-311):
  *   d[t,j] = (sum z_t^2 + sum e_j^2) - 2 z_t.e_j   in fp32, this association; idx[t] = argmin_j (lowest index wins)

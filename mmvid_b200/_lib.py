@@ -22,6 +22,11 @@ class EmbedSegment(C.Structure):
                 ("pos", _p), ("pad_value", _ll), ("pad_base", _ll), ("use_pad", _i)]
 
 
+class DecodeLayer(C.Structure):
+    _fields_ = [(n, _p) for n in ("ln1_w", "ln1_b", "in_w", "in_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc_w", "fc_b",
+                                  "proj_w", "proj_b", "kcache", "vcache")]
+
+
 class ConvParams(C.Structure):
     _fields_ = [("inp", _p), ("w", _p), ("bias", _p), ("residual", _p), ("out", _p)] + \
                [(n, _i) for n in ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad_t", "pad_l", "Ho", "Wo",
@@ -47,6 +52,8 @@ SIGNATURES = {
     "mmvid_decode_attention": (_i, [_p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _p]),
     "mmvid_linear_small_m": (_i, [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p]),
     "mmvid_kv_append": (_i, [_p, _ll, _p, _p, _i, _i, _i, _i, _p]),
+    "mmvid_artv_decode_workspace_floats": (_ll, [_i, _i, _i]),
+    "mmvid_artv_decode_step": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mmvid_vq_argmin": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
     "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),

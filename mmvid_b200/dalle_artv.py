@@ -271,6 +271,22 @@ class DALLE(nn.Module):
         if k_keep < self.num_image_tokens:
             raise NotImplementedError("filter_thres that prunes inside the image vocabulary")
         xt = torch.empty(B, 1, D, device=dev, dtype=torch.float32)
+        native = B <= 16
+        if native:
+            from . import _lib as L
+            import ctypes as C
+            lib = L.load()
+            layers = (L.DecodeLayer * len(blocks))()
+            for li, blk in enumerate(blocks):
+                e = layers[li]
+                e.ln1_w, e.ln1_b = blk.ln_1.weight.data_ptr(), blk.ln_1.bias.data_ptr()
+                e.in_w, e.in_b = blk.attn.in_proj_weight.data_ptr(), blk.attn.in_proj_bias.data_ptr()
+                e.out_w, e.out_b = blk.attn.out_proj.weight.data_ptr(), blk.attn.out_proj.bias.data_ptr()
+                e.ln2_w, e.ln2_b = blk.ln_2.weight.data_ptr(), blk.ln_2.bias.data_ptr()
+                e.fc_w, e.fc_b = blk.mlp.c_fc.weight.data_ptr(), blk.mlp.c_fc.bias.data_ptr()
+                e.proj_w, e.proj_b = blk.mlp.c_proj.weight.data_ptr(), blk.mlp.c_proj.bias.data_ptr()
+                e.kcache, e.vcache = kc[li].data_ptr(), vc[li].data_ptr()
+            ws = torch.empty(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev, dtype=torch.float32)
         for t in range(self.target_seq_len):
             # top_k keeps >= 1024 entries (k = 25888 at the default 0.5), so only the masked logits (-FLT_MAX -> prob 0)
             # are affected: softmax over the 1024 image logits is the whole distribution (dalle_artv.py:274-276)
@@ -289,6 +305,12 @@ class DALLE(nn.Module):
                                        pos=pos_table[t:t + 1])])
             h = xt.view(B, D)
             pos = P + t
+            if native:
+                # all 12 layers of this token issued from C (8 launches / layer, no Python in between)
+                L.check(lib.mmvid_artv_decode_step(layers, len(blocks), ops._ptr(h), ops._ptr(ws), B, D, H, S_max, pos,
+                                                   ops._stream()), "artv_decode_step")
+                logits = self._head_rows(h, lo, lo + self.num_image_tokens)
+                continue
             for li, blk in enumerate(blocks):
                 a = ops.layernorm(h, blk.ln_1.weight, blk.ln_1.bias, 1e-5)
                 qkv = ops.linear_small_m(a, blk.attn.in_proj_weight.detach(), blk.attn.in_proj_bias)
