@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
-      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 128);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 128);
     }
     mbar_init(all_done, 1);
     fence_barrier_init();
@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_ready[g]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);  // one arrival per warp (4 per group), not 128 serialised ones
       l += rs0 + rs1;
     }
     // every MMA of BOTH groups must have retired before K/V smem is recycled as the output staging area

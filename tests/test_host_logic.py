@@ -82,11 +82,28 @@ def test_random_erase_half_and_artv_pad_ids():
     assert a._allowed_range(a.control_seq_len) == (a.num_control_tokens, a.total_tokens)
 
 
-def test_training_forward_is_an_explicit_not_implemented():
+def test_training_forward_has_no_cpu_fallback():
     m, _ = build_bert(BERT_CASES["bert_tiny_nov"], device="cpu")
-    # no silent wrong answer: the forward kernels need CUDA, the training losses are not built yet
-    with pytest.raises((NotImplementedError, RuntimeError)):
+    # the training path runs on the CUDA kernels only: on CPU tensors it must fail loudly, never compute with torch
+    with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(2, 5, dtype=torch.long), target=torch.zeros(2, 3, 3, 32, 32), return_loss=True)
+
+
+def test_msm_mask_sampler_strategies_and_shapes():
+    import random
+    m, _ = build_bert(BERT_CASES["bert_tiny"], device="cpu")
+    np.random.seed(0); random.seed(0); torch.manual_seed(0)
+    for probs in ([1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]):
+        mask, nfm = m._sample_msm_masks(3, torch.device("cpu"), np.array(probs, dtype=float), [0.2, 0.5], 0.0)
+        assert mask.shape == (3, m.target_seq_len) and mask.dtype == torch.bool
+        if probs[1] == 1:  # strategy 2: everything masked, flagged as fully masked
+            assert not mask.any() and float(nfm.sum()) == 0
+        else:
+            assert float(nfm.sum()) == 3
+    # pc_prob = 1: at least one whole frame is kept as context
+    mask, _ = m._sample_msm_masks(2, torch.device("cpu"), np.array([0, 1.0, 0, 0]), [0.2, 0.5], 1.0)
+    per_frame = mask.view(2, m.num_targets, m.image_seq_len).all(dim=2)
+    assert per_frame.any(dim=1).all()
 
 
 def test_shard_bounds_cover_batch_exactly():
