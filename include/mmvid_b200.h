@@ -135,6 +135,12 @@ typedef struct {
 long long mmvid_artv_decode_workspace_floats(int B, int D, int H);
 int mmvid_artv_decode_step(const mmvid_decode_layer* host_layers, int n_layers, float* h, float* ws, int B, int D, int H,
                            int S_max, int pos, mmvid_stream_t stream);
+/* Persistent variant: ONE cooperative launch for all layers + the LN/image-logit head (grid-wide barriers between
+ * phases instead of ~110 launches per token).  B <= 8, n_layers <= 24.  head_w: [n_logits, D] rows of to_logits.1. */
+int mmvid_artv_decode_persistent(const mmvid_decode_layer* host_layers, int n_layers, float* h, float* ws,
+                                 const float* head_ln_w, const float* head_ln_b, const float* head_w,
+                                 const float* head_b, float* logits, int n_logits, int B, int D, int H, int S_max,
+                                 int pos, mmvid_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K14  VQ nearest-codeword lookup (taming/modules/vqvae/quantize.py:302-311):

@@ -194,7 +194,8 @@ extern "C" int mmvid_decode_attention(const float* q, long long q_bstride, const
 // workspace of mmvid_artv_decode_workspace_floats(B, D, H) floats.  Requires B <= 16.
 // ------------------------------------------------------------------------------------------------
 extern "C" long long mmvid_artv_decode_workspace_floats(int B, int D, int H) {
-  return (long long)B * (D + 3 * D + D + 4 * D) + (long long)B * H * 16 * 66;
+  const long long items = (long long)B * H * 16 > 4096 ? (long long)B * H * 16 : 4096;  // split-KV partial slots
+  return (long long)B * (D + 3 * D + D + 4 * D) + items * 66;
 }
 
 extern "C" int mmvid_artv_decode_step(const mmvid_decode_layer* layers, int n_layers, float* h, float* ws, int B, int D,
@@ -225,5 +226,256 @@ extern "C" int mmvid_artv_decode_step(const mmvid_decode_layer* layers, int n_la
     if ((rc = mmvid_linear_small_m(a, D, L.fc_w, D, L.fc_b, nullptr, 0, mid, 4 * D, B, 4 * D, D, MMVID_ACT_QUICKGELU, stream))) return rc;
     if ((rc = mmvid_linear_small_m(mid, 4 * D, L.proj_w, 4 * D, L.proj_b, h, D, h, D, B, D, 4 * D, MMVID_ACT_NONE, stream))) return rc;
   }
+  return MMVID_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent ART-V decode kernel: ONE cooperative launch runs all transformer layers (and the image-token head)
+// for the B newly sampled tokens.  Every SM streams its share of each weight matrix (the step is HBM-bound on the
+// 340 MB of fp32 weights + the K/V cache); phases are separated by grid-wide barriers instead of kernel launches:
+//   per layer:  [LN1 + QKV GEMV] | [cache append + single-query attention] | [out-proj + residual] |
+//               [LN2 + c_fc GEMV + QuickGELU] | [c_proj + residual]            then [LN + image-logit GEMV]
+// GEMV phases: the (LayerNorm-ed) B x K input rows are staged in shared memory by every block, each warp owns output
+// columns n = warp_global, warp_global + total_warps, ... and streams W[n, :] with 128-bit loads.
+// ------------------------------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int DEC_MAX_LAYERS = 24;
+constexpr int DEC_MAX_B = 8;
+
+struct DecodeParams {
+  mmvid_decode_layer layers[DEC_MAX_LAYERS];
+  int n_layers;
+  float* h;        // [B, D] in/out
+  float* qkv;      // [B, 3D]
+  float* att;      // [B, D]
+  float* mid;      // [B, 4D]
+  float* part;     // [B, H, Z, 66] split-KV partials (m, l, o[64])
+  const float *head_ln_w, *head_ln_b, *head_w, *head_b;  // head_w [n_logits, D] (image rows only), may be null
+  float* logits;   // [B, n_logits]
+  int n_logits;
+  int B, D, H, S_max, pos;
+};
+
+// stage `rows` = B x K (optionally LayerNorm-ed with gamma/beta) into shared memory.  All rows are fetched in ONE pass
+// (every load in flight at once); LayerNorm statistics are then computed from shared memory, one warp per row.
+__device__ void stage_rows(float* sm, const float* __restrict__ src, int B, int K, const float* gamma, const float* beta,
+                           float* red) {
+  (void)red;
+  const int n4 = (B * K) >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x)
+    reinterpret_cast<float4*>(sm)[i] = reinterpret_cast<const float4*>(src)[i];
+  __syncthreads();
+  if (gamma != nullptr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int b = warp; b < B; b += nw) {
+      float* x = sm + b * K;
+      float s = 0.f;
+      for (int c = lane; c < K; c += 32) s += x[c];
+      const float mean = warp_sum(s) / (float)K;
+      float q = 0.f;
+      for (int c = lane; c < K; c += 32) { const float d = x[c] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) / (float)K + 1e-5f);
+      for (int c = lane; c < K; c += 32) x[c] = (x[c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    }
+    __syncthreads();
+  }
+}
+
+template <int MAXB>
+__device__ void gemv_phase(const float* sm_rows, int B, int K, const float* __restrict__ W, const float* __restrict__ bias,
+                           const float* residual, long long ldr, float* out, long long ldo, int N, int act) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int total_warps = gridDim.x * warps_per_block;
+  const int lane = threadIdx.x & 31;
+  for (int n = warp_global; n < N; n += total_warps) {
+    const float4* w4 = reinterpret_cast<const float4*>(W + (long long)n * K);
+    float acc[MAXB];
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+      const float4 w = __ldg(w4 + k4);
+#pragma unroll
+      for (int b = 0; b < MAXB; ++b) {
+        if (b < B) {
+          const float4 a = *reinterpret_cast<const float4*>(sm_rows + b * K + k4 * 4);
+          acc[b] = fmaf(a.x, w.x, acc[b]); acc[b] = fmaf(a.y, w.y, acc[b]);
+          acc[b] = fmaf(a.z, w.z, acc[b]); acc[b] = fmaf(a.w, w.w, acc[b]);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+      const float v0 = warp_sum(acc[b]);
+      if (lane == 0 && b < B) {
+        float v = v0 + (bias ? bias[n] : 0.f);
+        v = apply_act(v, act);
+        if (residual) v += residual[b * ldr + n];
+        out[b * ldo + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) artv_decode_persistent_kernel(DecodeParams p) {
+  extern __shared__ float sm[];      // max(B * 4D staged rows, attention scratch)
+  __shared__ float red[32];
+  __shared__ float sm_m[8], sm_l[8];
+  __shared__ float sm_o[8][64];
+  cg::grid_group grid = cg::this_grid();
+  const int B = p.B, D = p.D, H = p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = p.pos + 1;
+  for (int li = 0; li < p.n_layers; ++li) {
+    const mmvid_decode_layer& L = p.layers[li];
+    // ---- phase 1: qkv = LN1(h) W_in^T + b
+    stage_rows(sm, p.h, B, D, L.ln1_w, L.ln1_b, red);
+    gemv_phase<DEC_MAX_B>(sm, B, D, L.in_w, L.in_b, nullptr, 0, p.qkv, 3 * D, 3 * D, MMVID_ACT_NONE);
+    grid.sync();
+    // ---- phase 2: append K,V of the new token; split-KV single-query attention: item = (b, h, z) owns keys
+    //      z*8 + warp, + 8Z, ... so that ALL blocks stream the cache (a (b,h)-per-block mapping leaves 2/3 of the SMs
+    //      idle and is latency-bound on dependent K -> softmax -> V loads); two keys are in flight per warp.
+    const int Z = max(1, (int)gridDim.x / (B * H));
+    for (int item = blockIdx.x; item < B * H * Z; item += gridDim.x) {
+      const int z = item % Z, bh = item / Z;
+      const int b = bh / H, hh = bh - b * H;
+      const float* row = p.qkv + (long long)b * 3 * D;
+      float* kb = L.kcache + ((long long)b * H + hh) * p.S_max * 64;
+      float* vb = L.vcache + ((long long)b * H + hh) * p.S_max * 64;
+      const float2 qv = *reinterpret_cast<const float2*>(row + hh * 64 + lane * 2);
+      const float2 knew = *reinterpret_cast<const float2*>(row + D + hh * 64 + lane * 2);
+      const float2 vnew = *reinterpret_cast<const float2*>(row + 2 * D + hh * 64 + lane * 2);
+      if (z == 0 && warp == 0) {  // the new token's K/V row (read back from registers below, so no ordering hazard)
+        *reinterpret_cast<float2*>(kb + (long long)p.pos * 64 + lane * 2) = knew;
+        *reinterpret_cast<float2*>(vb + (long long)p.pos * 64 + lane * 2) = vnew;
+      }
+      float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+      const int step = 8 * Z;
+      for (int s0 = z * 8 + warp; s0 < len; s0 += 4 * step) {
+        float2 kk[4], vv[4];
+        float dd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // 8 independent 256-byte row loads in flight per warp
+          const int su = s0 + u * step;
+          kk[u] = make_float2(0.f, 0.f); vv[u] = make_float2(0.f, 0.f);
+          if (su < len) {
+            kk[u] = (su == p.pos) ? knew : *reinterpret_cast<const float2*>(kb + (long long)su * 64 + lane * 2);
+            vv[u] = (su == p.pos) ? vnew : *reinterpret_cast<const float2*>(vb + (long long)su * 64 + lane * 2);
+          }
+        }
+        float mx = m;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          dd[u] = (s0 + u * step < len) ? warp_sum(qv.x * kk[u].x + qv.y * kk[u].y) * 0.125f : -INFINITY;
+          mx = fmaxf(mx, dd[u]);
+        }
+        const float alpha = expf(m - mx);
+        l *= alpha; o0 *= alpha; o1 *= alpha;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float pu = (dd[u] == -INFINITY) ? 0.f : expf(dd[u] - mx);
+          l += pu; o0 += pu * vv[u].x; o1 += pu * vv[u].y;
+        }
+        m = mx;
+      }
+      if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+      sm_o[warp][lane * 2] = o0; sm_o[warp][lane * 2 + 1] = o1;
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        float M = -INFINITY;
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w]);
+        float Ls = 0.f, O = 0.f;
+        for (int w = 0; w < 8; ++w) {
+          const float sc = (sm_m[w] == -INFINITY) ? 0.f : expf(sm_m[w] - M);
+          Ls += sm_l[w] * sc;
+          O += sm_o[w][threadIdx.x] * sc;
+        }
+        float* dst = p.part + (long long)item * 66;
+        dst[2 + threadIdx.x] = O;
+        if (threadIdx.x == 0) { dst[0] = M; dst[1] = Ls; }
+      }
+      __syncthreads();
+    }
+    grid.sync();
+    // ---- phase 3: h += att W_out^T + b   (att is combined from the split-KV partials while it is staged)
+    for (int i = threadIdx.x; i < B * D; i += blockDim.x) {
+      const int b = i / D, c = i - b * D, hh = c >> 6, d = c & 63;
+      const float* pp = p.part + ((long long)(b * H + hh) * Z) * 66;
+      float M = -INFINITY;
+      for (int z = 0; z < Z; ++z) M = fmaxf(M, pp[z * 66]);
+      float Ls = 0.f, O = 0.f;
+      for (int z = 0; z < Z; ++z) {
+        const float sc = (pp[z * 66] == -INFINITY) ? 0.f : expf(pp[z * 66] - M);
+        Ls += pp[z * 66 + 1] * sc;
+        O += pp[z * 66 + 2 + d] * sc;
+      }
+      sm[i] = O / Ls;
+    }
+    __syncthreads();
+    gemv_phase<DEC_MAX_B>(sm, B, D, L.out_w, L.out_b, p.h, D, p.h, D, D, MMVID_ACT_NONE);
+    grid.sync();
+    // ---- phase 4: mid = QuickGELU(LN2(h) W_fc^T + b)
+    stage_rows(sm, p.h, B, D, L.ln2_w, L.ln2_b, red);
+    gemv_phase<DEC_MAX_B>(sm, B, D, L.fc_w, L.fc_b, nullptr, 0, p.mid, 4 * D, 4 * D, MMVID_ACT_QUICKGELU);
+    grid.sync();
+    // ---- phase 5: h += mid W_proj^T + b
+    stage_rows(sm, p.mid, B, 4 * D, nullptr, nullptr, red);
+    gemv_phase<DEC_MAX_B>(sm, B, 4 * D, L.proj_w, L.proj_b, p.h, D, p.h, D, D, MMVID_ACT_NONE);
+    grid.sync();
+  }
+  if (p.head_w != nullptr) {
+    stage_rows(sm, p.h, B, D, p.head_ln_w, p.head_ln_b, red);
+    gemv_phase<DEC_MAX_B>(sm, B, D, p.head_w, p.head_b, nullptr, 0, p.logits, p.n_logits, p.n_logits, MMVID_ACT_NONE);
+  }
+}
+
+}  // namespace
+
+// Persistent variant of mmvid_artv_decode_step (+ fused LN + image-logit head).  B <= 8.
+extern "C" int mmvid_artv_decode_persistent(const mmvid_decode_layer* layers, int n_layers, float* h, float* ws,
+                                            const float* head_ln_w, const float* head_ln_b, const float* head_w,
+                                            const float* head_b, float* logits, int n_logits, int B, int D, int H,
+                                            int S_max, int pos, mmvid_stream_t stream) {
+  MMVID_REQUIRE(B >= 1 && B <= DEC_MAX_B, "1 <= B <= 8");
+  MMVID_REQUIRE(n_layers >= 1 && n_layers <= DEC_MAX_LAYERS, "1..24 layers");
+  MMVID_REQUIRE(D == H * 64 && D % 4 == 0, "D = 64 H");
+  MMVID_REQUIRE(pos >= 0 && pos < S_max, "pos in range");
+  DecodeParams p{};
+  for (int i = 0; i < n_layers; ++i) p.layers[i] = layers[i];
+  p.n_layers = n_layers;
+  p.h = h;
+  p.qkv = ws;
+  p.att = p.qkv + (long long)B * 3 * D;
+  p.mid = p.att + (long long)B * D;
+  p.part = p.mid + (long long)B * 4 * D;
+  p.head_ln_w = head_ln_w; p.head_ln_b = head_ln_b; p.head_w = head_w; p.head_b = head_b;
+  p.logits = logits; p.n_logits = n_logits;
+  p.B = B; p.D = D; p.H = H; p.S_max = S_max; p.pos = pos;
+  const size_t smem = (size_t)B * 4 * D * sizeof(float);
+  static int grid_blocks = 0;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t err = cudaFuncSetAttribute(artv_decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(artv_decode): %s", cudaGetErrorString(err));
+    smem_set = smem;
+    grid_blocks = 0;
+  }
+  if (grid_blocks == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artv_decode_persistent_kernel, 256, smem);
+    if (per_sm < 1) return fail(MMVID_ECUDA, "artv_decode: kernel does not fit on an SM%s");
+    grid_blocks = sms * (per_sm > 2 ? 2 : per_sm);
+  }
+  void* args[] = {&p};
+  cudaError_t err = cudaLaunchCooperativeKernel((void*)artv_decode_persistent_kernel, dim3(grid_blocks), dim3(256), args, smem,
+                                                to_stream(stream));
+  count_launch();
+  if (err != cudaSuccess) return fail(MMVID_ECUDA, "artv_decode_persistent launch: %s", cudaGetErrorString(err));
   return MMVID_OK;
 }

@@ -1,7 +1,7 @@
 // Flash attention v3 for sm_100a: TWO 128-query tiles per CTA ping-pong through the tensor core
 // (FA4-style schedule) so that the MMA pipe and the softmax (MUFU/FMA) pipes overlap inside one SM:
 //
-//   tensor core :  QK_A0 QK_B0 | PV_A0 QK_A1 PV_B0 QK_B1 | PV_A1 QK_A2 PV_B1 QK_B2 | ...
+//   tensor core :  QK_A0 . QK_B0 PV_A0 QK_A1 | PV_B0 QK_B1 | PV_A1 QK_A2 | PV_B1 QK_B2 | ...   (A and B in anti-phase)
 //   softmax grp A:        [ P_A0 ......... ][O_A0][ P_A1 ......... ][O_A1] ...
 //   softmax grp B:              [ P_B0 ......... ][O_B0][ P_B1 ......... ][O_B1] ...
 //
@@ -162,8 +162,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
+      // Anti-phase start: only tile A's first QK^T is issued up front; tile B's first QK^T goes out once A has
+      // finished its first softmax.  From then on A's exp2 phase overlaps B's MMAs and vice versa (if both tiles run
+      // in lockstep they fight for the MUFU pipe and then queue behind each other on the tensor pipe).
       issue_qk(0, 0);
-      issue_qk(1, 0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         const uint32_t kvph = (j >> 1) & 1;   // phase of the K/V stage barriers
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&p_ready[g], ph);                  // group g wrote P_j over S_g (and rescaled O_g if it had to)
           tc_fence_after();
+          if (j == 0 && g == 0) issue_qk(1, 0);        // delayed start of tile B (see above)
           issue_pv(g, st, j == 0);
           if (more) issue_qk(g, st ^ 1);               // S_g is free: PV_j (same issue stream) consumed P_j first
         }

@@ -429,6 +429,10 @@ int launch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiA
 
 }  // namespace
 
+extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
+                                const float* bias, const float* residual, long long ldr, void* C, int c_dtype,
+                                long long ldc, long long M, int N, int K, int act, int precision, int BN, cudaStream_t st);
+
 namespace {
 struct QkvReq { void* q; void* k; void* vt; int S, Spad, H; };
 thread_local QkvReq g_qkv{nullptr, nullptr, nullptr, 0, 0, 0};
@@ -447,6 +451,16 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
   if (M == 0 || N == 0) return MMVID_OK;
   const int BKE = tf32 ? 32 : 64;
   // tile width: keep >= ~1.5 waves of CTAs on 148 SMs (2 CTAs/SM) when the problem is small
+  {
+    // CTA-pair (cta_group::2, tc_gemm2.cu) kernel for long-K GEMMs (c_proj: K = 3072 measured 7-9 % faster than the
+    // single-CTA tile; short-K GEMMs are bounded by their output stream and gain nothing).  MMVID_GEMM_2CTA=128|256
+    // forces it everywhere, =1 disables it.
+    int bn2 = env_int("MMVID_GEMM_2CTA", 0);
+    if (bn2 == 0 && K >= 2048 && M >= 1024 && N >= 256) bn2 = 128;
+    if ((bn2 == 128 || bn2 == 256) && g_qkv.q == nullptr)
+      return mmvid_linear_tc2(A, a_dtype, lda, W, w_dtype, ldw, bias, residual, ldr, C, c_dtype, ldc, M, N, K, act, precision,
+                              bn2, st);
+  }
   const int BN = pick_bn(M, N);
   CUtensorMap tmA, tmB;
   {

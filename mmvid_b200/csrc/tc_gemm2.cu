@@ -1,0 +1,330 @@
+// 2-CTA tcgen05 GEMM (cta_group::2): a CTA pair (one TPC, cluster 2x1x1) owns a 256 x BN output tile.
+// Each CTA loads ITS 128 rows of A and ITS half (BN/2 rows) of the weight tile; one tcgen05.mma.cta_group::2 issued by
+// the leader CTA drives both SMs' tensor cores (M = 256) reading both CTAs' shared memory, so per CTA the operand
+// bytes per FLOP drop by 25 % (BN = 128) / 50 % (BN = 256) against the single-CTA 128 x 128 tile and the freed shared
+// memory deepens the TMA ring (8 / 6 stages).  Everything else mirrors tc_gemm.cu: persistent CTAs, two TMEM
+// accumulators, 8 epilogue warps per CTA with batched tcgen05.ld and swizzled smem transposes.
+//   full[s]      leader's barrier: leader expect_tx(bytes of BOTH CTAs); both CTAs' TMA loads complete_tx on it
+//   empty[s]     one per CTA: tcgen05.commit.cta_group::2 ... multicast arrives on both
+//   tmem_full[a] one per CTA (multicast commit);  tmem_empty[a] leader's barrier, 16 arrivals (8 warps x 2 CTAs)
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+
+using namespace mmvid;
+using namespace mmvid::tc;
+
+namespace {
+
+constexpr int BM = 128;  // rows per CTA (256 per pair)
+constexpr int G2_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_LD = 32;
+
+struct Epi2Args {
+  const float* bias; const float* residual; long long ldr;
+  void* C; long long ldc; int c_bf16;
+  long long M; int N, K, act;
+  int num_m_tiles /* 256-row tiles */, num_n_tiles;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");  // non-.aligned: role lanes arrive late
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {  // arrives on this barrier offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+
+template <int BN>
+constexpr int g2_stages() { return BN == 256 ? 6 : 8; }
+template <int BN>
+constexpr size_t g2_smem_bytes() {
+  return (size_t)g2_stages<BN>() * (BM * 128 + (BN / 2) * 128) + EPI_WARPS * 32 * EPI_LD * 4 + 1024 + 256;
+}
+
+template <bool TF32, int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epi2Args e) {
+  constexpr int STAGES = g2_stages<BN>();
+  extern __shared__ uint8_t smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = BM * 128, B_BYTES = (BN / 2) * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int BKE = TF32 ? 32 : 64;
+  float* epi_stage = reinterpret_cast<float*>(tiles + (size_t)STAGES * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_k = (e.K + BKE - 1) / BKE;
+  const int total_tiles = e.num_m_tiles * e.num_n_tiles;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_ptr, 2 * BN);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
+        const int m0 = mt * (2 * BM) + (int)rank * BM;          // my 128 rows of the pair's 256
+        const int n0 = nt * BN + (int)rank * (BN / 2);          // my half of the weight tile
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);  // bytes landing in BOTH CTAs
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[s]), 0);
+          uint8_t* a = tiles + s * STAGE_BYTES;
+          tma_load_2d_2sm(a, &tmA, full_leader, kb * BKE, m0);
+          tma_load_2d_2sm(a + A_BYTES, &tmB, full_leader, kb * BKE, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc<TF32>(2 * BM, BN);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
+        const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ss2<TF32>(d_tmem, desc_advance(a_desc, kk * 32), desc_advance(b_desc, kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
+          tc_commit2(&empty[s]);
+        }
+        tc_commit2(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int chalf = ew >> 2;
+    const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
+    const uint32_t st_wr = st_base + (uint32_t)(lane * EPI_LD * 4);
+    const int col = (lane & 7) * 4, rsub = lane >> 3;
+    const uint32_t st_rd_row = st_base + (uint32_t)(rsub * EPI_LD * 4);
+    const bool vec_ok = (e.N % 4 == 0) && (e.ldc % 4 == 0) && (!e.residual || e.ldr % 4 == 0);
+    constexpr int NCH = BN / 64;
+    uint32_t tile_iter = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
+      const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
+      const int m0 = mt * (2 * BM) + (int)rank * BM, n0 = nt * BN + chalf * (BN / 2);
+      const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+      float4 bias_r[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int n = n0 + c * 32 + col;
+        bias_r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias && n < e.N) {
+          if (vec_ok) bias_r[c] = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+          else {
+            bias_r[c].x = e.bias[n];
+            if (n + 1 < e.N) bias_r[c].y = e.bias[n + 1];
+            if (n + 2 < e.N) bias_r[c].z = e.bias[n + 2];
+            if (n + 3 < e.N) bias_r[c].w = e.bias[n + 3];
+          }
+        }
+      }
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
+      const long long m_first = (long long)m0 + q * 32 + rsub;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_src + c * 32, r);
+        tmem_ld_wait();
+        if (c == NCH - 1) {  // everything this warp needs is out of TMEM: release the accumulator (leader's barrier)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        }
+        if (n0 + c * 32 >= e.N) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(st_wr + (uint32_t)(((j ^ (lane & 7)) * 16)), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int n = n0 + c * 32 + col;
+        const bool n_ok = n < e.N;
+        float4 res[8], v[8];
+        if (vec_ok && e.residual) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long m = m_first + i * 4;
+            res[i] = (m < e.M && n_ok) ? *reinterpret_cast<const float4*>(e.residual + m * e.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = lds128(st_rd_row + (uint32_t)(i * 4 * EPI_LD * 4) + (uint32_t)((((lane & 7) ^ ((rsub + 4 * i) & 7)) * 16)));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long m = m_first + i * 4;
+          if (m >= e.M || !n_ok) continue;
+          float o[4] = {v[i].x + bias_r[c].x, v[i].y + bias_r[c].y, v[i].z + bias_r[c].z, v[i].w + bias_r[c].w};
+          if (e.act != MMVID_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = apply_act_fast(o[j], e.act);
+          }
+          if (vec_ok) {
+            if (e.residual) { o[0] += res[i].x; o[1] += res[i].y; o[2] += res[i].z; o[3] += res[i].w; }
+            if (e.c_bf16) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + m * e.ldc + n) = pk;
+            } else {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          } else {
+            for (int j = 0; j < 4; ++j) {
+              if (n + j >= e.N) break;
+              float x = o[j];
+              if (e.residual) x += e.residual[m * e.ldr + n + j];
+              if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.C)[m * e.ldc + n + j] = __float2bfloat16_rn(x);
+              else reinterpret_cast<float*>(e.C)[m * e.ldc + n + j] = x;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 2 * BN);
+  }
+}
+
+template <bool TF32, int BN>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStream_t st) {
+  static bool attr_set = false;
+  constexpr size_t smem = g2_smem_bytes<BN>();
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_tc2_kernel<TF32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(err));
+    attr_set = true;
+  }
+  e.num_m_tiles = (int)ceil_div<long long>(e.M, 2 * BM);
+  e.num_n_tiles = ceil_div(e.N, BN);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
+  const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
+  gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, e);
+  return check_launch("gemm_tc2");
+}
+
+}  // namespace
+
+// 2-CTA path of mmvid_linear (selected by mmvid_linear_tc: MMVID_GEMM_2CTA=BN in the environment, 128 or 256)
+extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
+                                const float* bias, const float* residual, long long ldr, void* C, int c_dtype,
+                                long long ldc, long long M, int N, int K, int act, int precision, int BN, cudaStream_t st) {
+  const bool tf32 = precision == MMVID_TF32;
+  const int esz = tf32 ? 4 : 2;
+  const int BKE = tf32 ? 32 : 64;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * esz};
+    uint32_t box[2] = {(uint32_t)BKE, (uint32_t)BM};
+    int rc = make_tensor_map(&tmA, A, a_dtype, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldw * esz};
+    uint32_t box[2] = {(uint32_t)BKE, (uint32_t)(BN / 2)};
+    int rc = make_tensor_map(&tmB, W, w_dtype, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  Epi2Args e{};
+  e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc; e.c_bf16 = c_dtype == MMVID_DT_BF16;
+  e.M = M; e.N = N; e.K = K; e.act = act;
+  if (BN == 256) return tf32 ? launch2<true, 256>(tmA, tmB, e, st) : launch2<false, 256>(tmA, tmB, e, st);
+  return tf32 ? launch2<true, 128>(tmA, tmB, e, st) : launch2<false, 128>(tmA, tmB, e, st);
+}

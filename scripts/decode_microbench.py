@@ -1,0 +1,41 @@
+"""Times one ART-V decode step (persistent cooperative kernel vs native per-layer launches) at fixed cache lengths."""
+import sys, ctypes as C, torch
+sys.path.insert(0, ".")
+from mmvid_b200 import _lib as L, ops
+lib = L.load()
+B, D, H, NL, S_max = 4, 768, 12, 12, 2369
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+def r(*s): return (torch.randn(*s, generator=g) * 0.02).to(dev)
+layers = (L.DecodeLayer * NL)()
+keep = []
+for li in range(NL):
+    t = dict(ln1_w=torch.ones(D, device=dev), ln1_b=torch.zeros(D, device=dev), in_w=r(3 * D, D), in_b=r(3 * D), out_w=r(D, D), out_b=r(D),
+             ln2_w=torch.ones(D, device=dev), ln2_b=torch.zeros(D, device=dev), fc_w=r(4 * D, D), fc_b=r(4 * D), proj_w=r(D, 4 * D), proj_b=r(D),
+             kcache=r(B, H, S_max, 64), vcache=r(B, H, S_max, 64))
+    keep.append(t)
+    for k, v in t.items(): setattr(layers[li], k, v.data_ptr())
+ws = torch.empty(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev)
+head_w, head_b = r(1024, D), r(1024)
+lnw, lnb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+logits = torch.empty(B, 1024, device=dev)
+h0 = r(B, D) * 50
+st = ops._stream()
+for pos in (400, 1300, 2300):
+    for name in ("persistent", "native"):
+        def call():
+            h = h0.clone()
+            if name == "persistent":
+                L.check(lib.mmvid_artv_decode_persistent(layers, NL, ops._ptr(h), ops._ptr(ws), ops._ptr(lnw), ops._ptr(lnb), ops._ptr(head_w),
+                                                         ops._ptr(head_b), ops._ptr(logits), 1024, B, D, H, S_max, pos, st))
+            else:
+                L.check(lib.mmvid_artv_decode_step(layers, NL, ops._ptr(h), ops._ptr(ws), B, D, H, S_max, pos, st))
+            return h
+        for _ in range(3): call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20): call()
+        e1.record(); torch.cuda.synchronize()
+        print(f"pos {pos} {name}: {e0.elapsed_time(e1) / 20 * 1000:.0f} us per step", flush=True)
+    a = None

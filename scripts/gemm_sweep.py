@@ -28,6 +28,13 @@ for (M,N,K,name) in json.loads(sys.argv[2]):
 print(json.dumps(res))
 '''
 QUICK = "--quick" in sys.argv
+if "--2cta" in sys.argv:
+    for prec in ("tf32", "bf16"):
+        for bn2 in (0, 128, 256):
+            env = dict(os.environ, MMVID_GEMM_2CTA=str(bn2))
+            r = subprocess.run([sys.executable, "-c", CHILD, prec, json.dumps(SHAPES)], env=env, capture_output=True, text=True, timeout=300)
+            print(prec, "2CTA BN", bn2, r.stdout.strip() or r.stderr[-800:], flush=True)
+    sys.exit(0)
 for prec in ("tf32", "bf16"):
     for bn in ((128, 256) if QUICK else (64, 128, 256)):
         for raster in ((0, 1) if QUICK else (0, 1, 2)):
