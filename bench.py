@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--mp-steps", type=int, default=20)
     ap.add_argument("--vae-precision", default=None, choices=["tf32", "fp32"],
                     help="VQGAN conv precision (default: tf32 tensor cores unless --precision fp32)")
-    ap.add_argument("--workload", default="bert", choices=["bert", "artv"],
+    ap.add_argument("--visuals", type=int, default=0, choices=[0, 1],
+                    help="bert/train: number of visual-control frames (1 = SURVEY config 4: cVAE-encoded frame, S=2371)")
+    ap.add_argument("--workload", default="bert", choices=["bert", "artv", "train"],
                     help="bert: BERT mask-predict generate_images (headline); artv: ART-V KV-cache autoregressive generate_images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="ncu mode: no warm-up, one step, no side measurements")
@@ -143,10 +145,17 @@ def run_reference_arm(args):
 def workload_config(args, per_gpu_batch):
     cfg = SHAPES[args.shape]
     fmap = cfg["image_size"] // 16
-    S = 1 + cfg["text_seq_len"] + 2 + cfg["num_targets"] * fmap * fmap
-    return {"workload": f"BERT.generate_images text-to-video shape {args.shape}: text {cfg['text_seq_len']} + "
-                        f"{cfg['num_targets']}x({fmap}x{fmap}) video tokens (S={S}), ViT-B/32-shaped transformer 768x12, "
-                        f"mask-predict T={args.mp_steps} beam 1 + VQGAN f16 decode @{cfg['image_size']}px",
+    V = getattr(args, "visuals", 0)
+    S = 1 + cfg["text_seq_len"] + V * fmap * fmap + 2 + cfg["num_targets"] * fmap * fmap
+    name = (f"BERT.generate_images text-to-video shape {args.shape}: text {cfg['text_seq_len']} + "
+            f"{cfg['num_targets']}x({fmap}x{fmap}) video tokens (S={S}), ViT-B/32-shaped transformer 768x12, "
+            f"mask-predict T={args.mp_steps} beam 1 + VQGAN f16 decode @{cfg['image_size']}px")
+    if V:
+        name += f", {V} visual-control frame(s) through the cVAE encoder"
+    if getattr(args, "workload", "bert") == "train":
+        name = (f"BERT.forward(return_loss=True, rel=True, vid=True) + backward + clip_grad_norm_ + Adam, shape {args.shape} "
+                f"(S={S}): 2 VQGAN encodes of the {cfg['num_targets']} target frames, 3 transformer passes (train.py:298-325)")
+    return {"workload": name,
             "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "seq_len": S,
             "parallelism": f"replicas x{args.gpus}, batch split, one all-gather of frames",
             "precision": args.precision,
@@ -211,6 +220,8 @@ def build_artv(args, device):
 def build_model(args, device):
     if args.workload == "artv":
         return build_artv(args, device)
+    if args.workload == "train" and args.precision == "bf16":
+        raise SystemExit("training runs the tf32 or fp32 path (bf16 activations are an inference-only mode)")
     from mmvid_b200.dalle_bert import BERT
     from mmvid_b200.vae import VQGanVAE1024
     cfg = SHAPES[args.shape]
@@ -220,10 +231,16 @@ def build_model(args, device):
     vae.image_size = cfg["image_size"]
     # default VQ init U(+-1/1024) is degenerate for decoding; use unit-scale codes (random-init weights, no checkpoint)
     vae.model.quantize.embedding.weight.data.normal_(0, 0.3)
-    model = BERT(dim=DIM, vae=vae, cvae=None, num_text_tokens=VOCAB, text_seq_len=cfg["text_seq_len"],
-                 which_transformer="openai_clip_visual", num_visuals=0, num_targets=cfg["num_targets"],
+    cvae = None
+    if args.visuals:
+        cvae = VQGanVAE1024(vae_path=None, image_size=cfg["image_size"], precision=vprec)
+        cvae.image_size = cfg["image_size"]
+        cvae.model.quantize.embedding.weight.data.normal_(0, 0.3)
+    model = BERT(dim=DIM, vae=vae, cvae=cvae, num_text_tokens=VOCAB, text_seq_len=cfg["text_seq_len"],
+                 which_transformer="openai_clip_visual", num_visuals=args.visuals, num_targets=cfg["num_targets"],
                  openai_clip_path=None, transformer_layers=LAYERS, precision=args.precision, sampling_mode="batched")
-    return model.to(device).eval()
+    model = model.to(device)
+    return model.train() if args.workload == "train" else model.eval()
 
 
 def kernel_roofline(model, args, peaks, S, B):
@@ -297,7 +314,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     from mmvid_b200 import _lib
-    from mmvid_b200.parallel import all_gather_variable
+    from mmvid_b200.parallel import all_gather_variable, all_reduce_gradients
     peaks = load_peaks()
     cfg = SHAPES[args.shape]
     model = build_model(args, dev)
@@ -316,16 +333,51 @@ def run_ours(args):
     artv_visual = None
     if args.workload == "artv":
         artv_visual = torch.rand(B, 1, 3, cfg["image_size"], cfg["image_size"], generator=g).to(dev)
+    host_visual = dev_visual = None
+    if args.visuals and args.workload != "artv":
+        host_visual = torch.rand(B, 1, 3, cfg["image_size"], cfg["image_size"], generator=g).pin_memory()
+        dev_visual = host_visual.to(dev)
+    h2d_bytes = host_text.numel() * 8 + (host_visual.numel() * 4 if host_visual is not None else 0)
+    d2h_bytes = host_frames.numel() * 4
+    train = args.workload == "train"
+    if train:
+        # train.py:298-325 with the CLI defaults (utils_args.py:357-410): Adam lr 1e-4, clip 1.0, betas 7 / 0.5 / 0.5
+        import random
+        import numpy as np
+        from mmvid_b200 import optim as FO
+        np.random.seed(42 + rank)
+        random.seed(42 + rank)
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = FO.FusedAdam(params, lr=1e-4, weight_decay=0.0)
+        host_target = torch.rand(B, cfg["num_targets"], 3, cfg["image_size"], cfg["image_size"], generator=g).pin_memory()
+        dev_target = host_target.to(dev)
+        host_loss = torch.empty(1).pin_memory()
+        h2d_bytes += host_target.numel() * 4
+        d2h_bytes = 4
 
     def step(e2e):
         if e2e:
             text = host_text.to(dev, non_blocking=True)
+            visual = host_visual.to(dev, non_blocking=True) if host_visual is not None else None
         else:
-            text = dev_text
+            text, visual = dev_text, dev_visual
+        if train:
+            target = host_target.to(dev, non_blocking=True) if e2e else dev_target
+            l_msm, l_rel, l_vid = model(text, visual=visual, target=target, return_loss=True, rel=True, vid=True)
+            loss = 7.0 * l_msm + 0.5 * l_rel + 0.5 * l_vid
+            opt.zero_grad()
+            loss.backward()
+            if world > 1:
+                all_reduce_gradients(params)  # DDP-equivalent gradient averaging (train.py:32), NCCL over NVLink
+            FO.clip_grad_norm_(params, 1.0)
+            opt.step()
+            if e2e:
+                host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            return loss
         if args.workload == "artv":
             images, _, seq = model.generate_images(text, visual=artv_visual)
         else:
-            images, _, seq = model.generate_images(text, mask_predict_steps=args.mp_steps, dynamic=False)
+            images, _, seq = model.generate_images(text, visual=visual, mask_predict_steps=args.mp_steps, dynamic=False)
         if world > 1:
             images = all_gather_variable(images.contiguous(), [B] * world)
         if e2e:
@@ -368,8 +420,8 @@ def run_ours(args):
     total_tokens = tokens_per_sample * B * world * args.steps
     value, e2e_value = total_tokens / t_dev, total_tokens / t_e2e
     if rank == 0:
-        S = 1 + cfg["text_seq_len"] + 2 + tokens_per_sample
-        kr = kernel_roofline(model, args, peaks, S, B) if args.workload == "bert" else {"gemm_c_fc": dict(ms=0.0, tflops=0.0)}
+        S = 1 + cfg["text_seq_len"] + args.visuals * fmap * fmap + 2 + tokens_per_sample
+        kr = kernel_roofline(model, args, peaks, S, B) if args.workload in ("bert", "train") else {"gemm_c_fc": dict(ms=0.0, tflops=0.0)}
         dom = "attention" if "attention" in kr else "gemm_c_fc"
         peak = peaks["bf16_tflops"]
         traffic = None
@@ -386,17 +438,19 @@ def run_ours(args):
                 "frac_of_half_rate": kr[dom]["tflops"] / (peak / 2) if args.precision == "tf32" else None,
                 "kernels": kr}
         out = {
-            "metric": "video-tokens/sec (BERT.generate_images, mask-predict T=%d + VQGAN decode)" % args.mp_steps,
+            "metric": {"bert": "video-tokens/sec (BERT.generate_images, mask-predict T=%d + VQGAN decode)" % args.mp_steps,
+                       "artv": "video-tokens/sec (DALLE.generate_images, ART-V, KV-cache decode + VQGAN decode)",
+                       "train": "video-tokens/sec (BERT training step: forward + backward + clip + Adam)"}[args.workload],
             "value": value, "unit": "video-tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"tf32": "tf32 (fp32 storage, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
             "data": "synthetic", "config": dict(workload_config(args, B), **({"workload": "DALLE(ART-V).generate_images with KV cache, shape " + args.shape + ": prefix 1+L+n, " + str(tokens_per_sample) + " decode steps, batch " + str(B)} if args.workload == "artv" else {})),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "video-tokens/s", "h2d_bytes_per_step": host_text.numel() * 8,
-                    "d2h_bytes_per_step": host_frames.numel() * 4, "ms_per_step": 1000.0 * t_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": "video-tokens/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000.0 * t_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "bert":
             out["cpu_baseline"] = cpu_reference_tokens_per_s(args.shape, args.mp_steps, n_fwd=2)
         print(json.dumps(out))
     if world > 1:

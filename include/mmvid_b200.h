@@ -223,6 +223,32 @@ int mmvid_embed_backward(const float* dx, int B, int S, int D, const mmvid_embed
                          float* d_table2, float* d_pos, mmvid_stream_t stream);
 int mmvid_transpose2d(const float* in, float* out, int R, int C, mmvid_stream_t stream);
 
+/* K18 optimiser step (train.py:322-325: opt.zero_grad / loss.backward / clip_grad_norm_ / opt.step; optimisers
+ * utils_train.py:167-181: torch.optim.Adam(lr, weight_decay) or AdamW(betas=(0.9, 0.95))).  Multi-tensor: the caller
+ * builds, once, a device table with one record per parameter tensor and a chunk map (chunk c covers elements
+ * [chunk_index[c]*chunk_elems, +chunk_elems) of tensor chunk_tensor[c]); every call is one launch over all chunks.
+ * A record with g == NULL is skipped (parameter without gradient).  All tensors fp32, contiguous. */
+typedef struct {
+  void* p;        /* parameter                */
+  const void* g;  /* gradient (may be NULL)   */
+  void* m;        /* exp_avg                  */
+  void* v;        /* exp_avg_sq               */
+  long long n;    /* elements                 */
+  long long skipped; /* optimiser steps this tensor had no gradient for: its own step is `step - skipped` */
+} mmvid_adam_tensor;
+/* total_sq[0] = sum over all gradients of g^2; deterministic (per-chunk partials, ordered finalize).
+ * partial_dev: n_chunks floats of scratch. */
+int mmvid_grad_sqnorm(const mmvid_adam_tensor* table_dev, const int* chunk_tensor_dev, const int* chunk_index_dev,
+                      int n_chunks, int chunk_elems, float* partial_dev, float* total_sq_dev, mmvid_stream_t stream);
+/* torch.nn.utils.clip_grad_norm_: g *= min(1, max_norm / (sqrt(total_sq) + 1e-6)), in place, no host sync */
+int mmvid_grad_clip(const mmvid_adam_tensor* table_dev, const int* chunk_tensor_dev, const int* chunk_index_dev,
+                    int n_chunks, int chunk_elems, const float* total_sq_dev, float max_norm, mmvid_stream_t stream);
+/* Adam (decoupled_weight_decay = 0) / AdamW (1) update of step `step` (1-based), torch semantics (eps outside the
+ * bias-corrected sqrt, no amsgrad) */
+int mmvid_adam_step(const mmvid_adam_tensor* table_dev, const int* chunk_tensor_dev, const int* chunk_index_dev,
+                    int n_chunks, int chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int decoupled_weight_decay, int step, mmvid_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,10 @@ class DecodeLayer(C.Structure):
                                   "proj_w", "proj_b", "kcache", "vcache")]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("p", _p), ("g", _p), ("m", _p), ("v", _p), ("n", _ll), ("skipped", _ll)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [("inp", _p), ("w", _p), ("bias", _p), ("residual", _p), ("out", _p)] + \
                [(n, _i) for n in ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad_t", "pad_l", "Ho", "Wo",
@@ -74,6 +78,9 @@ SIGNATURES = {
     "mmvid_cross_entropy": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p]),
     "mmvid_embed_backward": (_i, [_p, _i, _i, _i, C.POINTER(EmbedSegment), _p, _p, _p, _p]),
     "mmvid_transpose2d": (_i, [_p, _p, _i, _i, _p]),
+    "mmvid_grad_sqnorm": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
+    "mmvid_grad_clip": (_i, [_p, _p, _p, _i, _i, _p, _f, _p]),
+    "mmvid_adam_step": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _f, _i, _i, _p]),
 }
 
 _lib = None

@@ -297,7 +297,10 @@ class DALLE(nn.Module):
             head_w = lin.weight.detach()[lo:lo + self.num_image_tokens]
             head_b = lin.bias.detach()[lo:lo + self.num_image_tokens]
             logits_buf = torch.empty(B, self.num_image_tokens, device=dev, dtype=torch.float32)
+        trace = kwargs.get("logits_trace")  # optional list: receives the [B, 1024] image logits of every step (tests)
         for t in range(self.target_seq_len):
+            if trace is not None:
+                trace.append(logits.clone())
             # top_k keeps >= 1024 entries (k = 25888 at the default 0.5), so only the masked logits (-FLT_MAX -> prob 0)
             # are affected: softmax over the 1024 image logits is the whole distribution (dalle_artv.py:274-276)
             probs_img = ops.softmax_logits(logits / temperature if temperature != 1.0 else logits)

@@ -65,3 +65,39 @@ def generate_images_sharded(model, text, visual=None, **gen_kwargs):
         per = seq.shape[0] // max(t_loc.shape[0], 1)
         seq = all_gather_variable(seq.contiguous(), [s * per for s in sizes])
     return images, extra, seq
+
+
+@torch.no_grad()
+def all_reduce_gradients(params, bucket_bytes=64 << 20):
+    """Data-parallel training (train.py:32 wraps the model in DDP): average `.grad` over ranks with one all-reduce per
+    flat bucket of up to `bucket_bytes` (few large NVLink/NVSwitch collectives instead of one per tensor), in parameter
+    order so every rank builds identical buckets.  Parameters without a gradient on this rank contribute zeros."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    params = [p for p in params if p.requires_grad]
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = flat[off:off + n].view_as(p).clone()
+            else:
+                p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+        bucket, size = [], 0
+
+    for p in params:
+        bucket.append(p)
+        size += p.numel() * p.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()

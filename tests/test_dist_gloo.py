@@ -47,3 +47,40 @@ def test_sharded_generation_gathers_global_batch(n):
         p.join(30)
     for rank, ok_i, ok_s, shape in res:
         assert ok_i and ok_s and shape[0] == n
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmvid_b200.parallel import all_reduce_gradients
+    g = torch.Generator().manual_seed(3)
+    shapes = [(5, 7), (3,), (11, 2, 2), (1,)]
+    base = [torch.randn(*s, generator=g) for s in shapes]
+    params = [torch.nn.Parameter(torch.zeros(*s)) for s in shapes]
+    for i, (p, b) in enumerate(zip(params, base)):
+        if not (rank == 1 and i == 2):            # rank 1 has no gradient for parameter 2
+            p.grad = b * (rank + 1)
+    all_reduce_gradients(params, bucket_bytes=64)  # tiny buckets: several collectives
+    ok = True
+    for i, (p, b) in enumerate(zip(params, base)):
+        want = b * (1.5 if i != 2 else 0.5)         # mean of (1, 2) x b; parameter 2: (1 + 0) / 2
+        ok = ok and bool(torch.allclose(p.grad, want, atol=1e-6))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_averages_over_ranks():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert all(ok for _, ok in res)

@@ -63,8 +63,11 @@ def test_training_losses_and_gradients_match_oracle_autograd(name, prec, tol_los
     assert checked > 20
 
 
-def test_reference_train_call_signature_and_optimizer_step():
-    """The call train.py:298-325 makes: losses -> weighted sum -> backward -> clip -> Adam step; loss must go down."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_reference_train_call_signature_and_optimizer_step(fused):
+    """The call train.py:298-325 makes: losses -> weighted sum -> backward -> clip -> Adam step; loss must go down.
+    fused=False: torch's own Adam / clip on the drop-in module; fused=True: the library's multi-tensor kernels."""
+    from mmvid_b200 import optim as FO
     cfg = BERT_CASES["bert_tiny"]
     model, _ = build_bert(cfg, precision="tf32")
     model.train()
@@ -76,7 +79,8 @@ def test_reference_train_call_signature_and_optimizer_step():
     text = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], 1).cuda()
     visual = synth.synth_frames(B, cfg["num_visuals"], cfg["image_size"], 2).cuda()
     frames = synth.synth_frames(B, cfg["num_targets"], cfg["image_size"], 3).cuda()
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=3e-3)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = FO.FusedAdam(params, lr=3e-3) if fused else torch.optim.Adam(params, lr=3e-3)
     hist = []
     for it in range(6):
         np.random.seed(1)
@@ -88,8 +92,50 @@ def test_reference_train_call_signature_and_optimizer_step():
         loss = 7 * loss_msm + 0.5 * loss_rel + 0.5 * loss_vid
         opt.zero_grad()
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        if fused:
+            FO.clip_grad_norm_(params, 1.0)
+        else:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         hist.append(float(loss))
     print("training loss history:", [round(h, 4) for h in hist])
     assert all(np.isfinite(hist)) and hist[-1] < hist[0]
+
+
+@pytest.mark.parametrize("kind,wd", [("adam", 0.0), ("adam", 0.01), ("adamw", 0.05)])
+def test_fused_adam_and_clip_match_torch_optimisers(kind, wd):
+    """train.py:322-325 step: clip_grad_norm_ + Adam/AdamW, multi-tensor kernels vs torch's own CPU optimisers
+    (the reference's definition, utils_train.py:167-181)."""
+    from mmvid_b200 import optim as FO
+    g = torch.Generator().manual_seed(5)
+    shapes = [(768, 768), (3, 5, 7), (1,), (70001,), (1026, 64), (131072,)]
+    ref = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref]
+    kw = dict(lr=3e-3, weight_decay=wd)
+    if kind == "adam":
+        o_ref, o_ours = torch.optim.Adam(ref, **kw), FO.FusedAdam(ours, **kw)
+    else:
+        o_ref, o_ours = torch.optim.AdamW(ref, betas=(0.9, 0.95), **kw), FO.FusedAdamW(ours, betas=(0.9, 0.95), **kw)
+    for it in range(4):
+        o_ref.zero_grad()
+        o_ours.zero_grad()
+        for i, (a, b) in enumerate(zip(ref, ours)):
+            if it == 2 and i == 1:
+                continue  # a parameter without a gradient this step
+            gr = torch.randn(a.shape, generator=g) * (10.0 if it % 2 == 0 else 0.01)  # clipped / not clipped
+            a.grad = gr.clone()
+            b.grad = gr.cuda()
+        n_ref = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        n_ours = FO.clip_grad_norm_(ours, 1.0)
+        assert abs(float(n_ours) - float(n_ref)) <= 1e-5 * float(n_ref)
+        for a, b in zip(ref, ours):
+            if a.grad is not None:
+                assert relerr(b.grad.cpu(), a.grad) < 1e-5  # clip coefficient: sqrt(sum g^2) vs torch's norm of norms
+        o_ref.step()
+        o_ours.step()
+        for a, b in zip(ref, ours):
+            assert (b.detach().cpu() - a.detach()).abs().max() < 2e-6, (it, a.shape)
+    sd = o_ours.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}  # torch's checkpoint layout (train.py:352)
+    o_ref.load_state_dict({"state": {k: {kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
+                                     for k, v in sd["state"].items()}, "param_groups": sd["param_groups"]})
