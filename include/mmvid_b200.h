@@ -223,6 +223,10 @@ int mmvid_embed_backward(const float* dx, int B, int S, int D, const mmvid_embed
                          float* d_table2, float* d_pos, mmvid_stream_t stream);
 int mmvid_transpose2d(const float* in, float* out, int R, int C, mmvid_stream_t stream);
 
+/* Profiling hook (not part of the data path): CTA (0,0) of every following mmvid_attention launch writes clock64()
+ * stamps of its pipeline events into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/att_trace.py. */
+int mmvid_debug_attention_trace(unsigned long long* dev_buf);
+
 /* K18 optimiser step (train.py:322-325: opt.zero_grad / loss.backward / clip_grad_norm_ / opt.step; optimisers
  * utils_train.py:167-181: torch.optim.Adam(lr, weight_decay) or AdamW(betas=(0.9, 0.95))).  Multi-tensor: the caller
  * builds, once, a device table with one record per parameter tensor and a chunk map (chunk c covers elements

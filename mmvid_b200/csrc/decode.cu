@@ -10,41 +10,79 @@ using namespace mmvid;
 
 namespace {
 
-// One warp per output column n: streams W[n, :] with 128-bit loads, keeps M accumulators.
+// One slice of a GEMV column: `units` of 128 floats (32 lanes x float4) of weight row w4, 8 units (= 8 independent
+// 16-byte loads per lane, 4 KB per warp) issued before the first FMA so that the row streams at memory speed instead of
+// one L2/HBM round trip per 512 bytes.  a(b, k4) returns the float4 of activation row b at float4 index k4.
+template <int MAXB, typename ALoad>
+__device__ __forceinline__ void gemv_slice(const float4* __restrict__ w4, int k4_end, int u0, int u1, int lane, int B,
+                                           ALoad a, float (&acc)[MAXB]) {
+  for (int u = u0; u < u1; u += 8) {
+    float4 w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k4 = (u + j) * 32 + lane;
+      w[j] = (u + j < u1 && k4 < k4_end) ? __ldg(w4 + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k4 = (u + j) * 32 + lane;
+      if (u + j < u1 && k4 < k4_end) {
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+          if (b < B) {
+            const float4 x = a(b, k4);
+            acc[b] = fmaf(x.x, w[j].x, acc[b]); acc[b] = fmaf(x.y, w[j].y, acc[b]);
+            acc[b] = fmaf(x.z, w[j].z, acc[b]); acc[b] = fmaf(x.w, w[j].w, acc[b]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Small-M linear: KS warps of a block share one output column (K split KS ways, combined through shared memory in a
+// fixed order), the other 8/KS column groups take neighbouring columns; every warp streams its weight slice with 8
+// independent 16-byte loads in flight per lane.  The host picks KS so that narrow layers still fill the 148 SMs.
 template <int MAXM>
 __global__ void __launch_bounds__(256) linear_small_m_kernel(const float* __restrict__ A, long long lda,
                                                             const float* __restrict__ W, long long ldw,
                                                             const float* __restrict__ bias,
                                                             const float* __restrict__ residual, long long ldr,
                                                             float* __restrict__ C, long long ldc, int M, int N, int K,
-                                                            int act) {
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
+                                                            int act, int KS) {
+  __shared__ float sm_part[8][MAXM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cols_per_block = 8 / KS;
+  const int sub = warp % KS, cw = warp / KS;
+  const int n = blockIdx.x * cols_per_block + cw;
+  const int units = (K + 127) >> 7;
+  const int upw = (units + KS - 1) / KS;
   float acc[MAXM];
 #pragma unroll
   for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
-  const float4* w4 = reinterpret_cast<const float4*>(W + (long long)n * ldw);
-  for (int k4 = lane; k4 < K / 4; k4 += 32) {
-    const float4 w = __ldg(w4 + k4);
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m) {
-      if (m < M) {
-        const float4 a = *reinterpret_cast<const float4*>(A + m * lda + k4 * 4);
-        acc[m] = fmaf(a.x, w.x, acc[m]); acc[m] = fmaf(a.y, w.y, acc[m]);
-        acc[m] = fmaf(a.z, w.z, acc[m]); acc[m] = fmaf(a.w, w.w, acc[m]);
-      }
-    }
+  if (n < N) {
+    gemv_slice<MAXM>(reinterpret_cast<const float4*>(W + (long long)n * ldw), K >> 2, sub * upw, min(units, (sub + 1) * upw),
+                     lane, M, [&](int m, int k4) { return __ldg(reinterpret_cast<const float4*>(A + m * lda) + k4); }, acc);
   }
+  float mine = 0.f;  // lane m keeps row m's total
 #pragma unroll
   for (int m = 0; m < MAXM; ++m) {
-    float v = warp_sum(acc[m]);
-    if (lane == 0 && m < M) {
-      if (bias) v += bias[n];
-      v = apply_act(v, act);
-      if (residual) v += residual[m * ldr + n];
-      C[m * ldc + n] = v;
+    const float v = warp_sum(acc[m]);
+    if (lane == m) mine = v;
+  }
+  if (KS > 1) {
+    if (lane < MAXM) sm_part[warp][lane] = mine;
+    __syncthreads();
+    if (sub == 0 && lane < M) {
+      mine = 0.f;
+      for (int s2 = 0; s2 < KS; ++s2) mine += sm_part[warp + s2][lane];
     }
+  }
+  if (sub == 0 && lane < M && n < N) {
+    float v = mine + (bias ? bias[n] : 0.f);
+    v = apply_act(v, act);
+    if (residual) v += residual[lane * ldr + n];
+    C[lane * ldc + n] = v;
   }
 }
 
@@ -162,11 +200,15 @@ extern "C" int mmvid_linear_small_m(const float* A, long long lda, const float* 
                                     int act, mmvid_stream_t stream) {
   MMVID_REQUIRE(M >= 1 && M <= 16, "1 <= M <= 16");
   MMVID_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0, "K, lda, ldw multiples of 4");
-  dim3 grid(ceil_div(N, 8));
+  // K split: enough (column, slice) warps for ~2 blocks per SM, at most one slice per 128-float unit
+  const int units = (K + 127) / 128;
+  int KS = 1;
+  while (KS < 8 && (long long)N * KS < 8LL * 2 * 148 && units >= KS * 2) KS *= 2;
+  dim3 grid(ceil_div(N, 8 / KS));
   cudaStream_t st = to_stream(stream);
-  if (M <= 4) linear_small_m_kernel<4><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act);
-  else if (M <= 8) linear_small_m_kernel<8><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act);
-  else linear_small_m_kernel<16><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act);
+  if (M <= 4) linear_small_m_kernel<4><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act, KS);
+  else if (M <= 8) linear_small_m_kernel<8><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act, KS);
+  else linear_small_m_kernel<16><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, act, KS);
   return check_launch("linear_small_m");
 }
 
@@ -285,39 +327,52 @@ __device__ void stage_rows(float* sm, const float* __restrict__ src, int B, int 
   }
 }
 
+// out[b, n] = act(rows[b, :] . W[n, :] + bias[n]) (+ residual[b, n]) for all N columns, spread over the whole grid.
+// KS consecutive warps of a block share one column (K split KS ways, partial sums combined through shared memory in a
+// fixed order: deterministic) so that narrow layers (N = D) still occupy every SM.
 template <int MAXB>
 __device__ void gemv_phase(const float* sm_rows, int B, int K, const float* __restrict__ W, const float* __restrict__ bias,
-                           const float* residual, long long ldr, float* out, long long ldo, int N, int act) {
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int total_warps = gridDim.x * warps_per_block;
-  const int lane = threadIdx.x & 31;
-  for (int n = warp_global; n < N; n += total_warps) {
-    const float4* w4 = reinterpret_cast<const float4*>(W + (long long)n * K);
+                           const float* residual, long long ldr, float* out, long long ldo, int N, int act,
+                           float (*sm_part)[MAXB]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_warps = gridDim.x * 8;
+  const int units = (K + 127) >> 7;
+  int KS = 1;
+  while (KS < 8 && N * (KS * 2) <= total_warps && units >= KS * 2) KS *= 2;
+  const int cols_per_block = 8 / KS;
+  const int upw = (units + KS - 1) / KS;
+  const int sub = warp % KS, cw = warp / KS;
+  for (int c0 = blockIdx.x * cols_per_block; c0 < N; c0 += gridDim.x * cols_per_block) {
+    const int n = c0 + cw;
     float acc[MAXB];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
-    for (int k4 = lane; k4 < K / 4; k4 += 32) {
-      const float4 w = __ldg(w4 + k4);
-#pragma unroll
-      for (int b = 0; b < MAXB; ++b) {
-        if (b < B) {
-          const float4 a = *reinterpret_cast<const float4*>(sm_rows + b * K + k4 * 4);
-          acc[b] = fmaf(a.x, w.x, acc[b]); acc[b] = fmaf(a.y, w.y, acc[b]);
-          acc[b] = fmaf(a.z, w.z, acc[b]); acc[b] = fmaf(a.w, w.w, acc[b]);
-        }
-      }
+    if (n < N) {
+      gemv_slice<MAXB>(reinterpret_cast<const float4*>(W + (long long)n * K), K >> 2, sub * upw, min(units, (sub + 1) * upw),
+                       lane, B,
+                       [&](int b, int k4) { return *reinterpret_cast<const float4*>(sm_rows + b * K + k4 * 4); }, acc);
     }
+    float mine = 0.f;  // lane b keeps row b's total
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) {
-      const float v0 = warp_sum(acc[b]);
-      if (lane == 0 && b < B) {
-        float v = v0 + (bias ? bias[n] : 0.f);
-        v = apply_act(v, act);
-        if (residual) v += residual[b * ldr + n];
-        out[b * ldo + n] = v;
+      const float v = warp_sum(acc[b]);
+      if (lane == b) mine = v;
+    }
+    if (KS > 1) {
+      if (lane < MAXB) sm_part[warp][lane] = mine;
+      __syncthreads();
+      if (sub == 0 && lane < B) {
+        mine = 0.f;
+        for (int s2 = 0; s2 < KS; ++s2) mine += sm_part[warp + s2][lane];
       }
     }
+    if (sub == 0 && lane < B && n < N) {
+      float v = mine + (bias ? bias[n] : 0.f);
+      v = apply_act(v, act);
+      if (residual) v += residual[lane * ldr + n];
+      out[lane * ldo + n] = v;
+    }
+    if (KS > 1) __syncthreads();
   }
 }
 
@@ -326,6 +381,7 @@ __global__ void __launch_bounds__(256) artv_decode_persistent_kernel(DecodeParam
   __shared__ float red[32];
   __shared__ float sm_m[8], sm_l[8];
   __shared__ float sm_o[8][64];
+  __shared__ float sm_part[8][DEC_MAX_B];
   cg::grid_group grid = cg::this_grid();
   const int B = p.B, D = p.D, H = p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -334,7 +390,7 @@ __global__ void __launch_bounds__(256) artv_decode_persistent_kernel(DecodeParam
     const mmvid_decode_layer& L = p.layers[li];
     // ---- phase 1: qkv = LN1(h) W_in^T + b
     stage_rows(sm, p.h, B, D, L.ln1_w, L.ln1_b, red);
-    gemv_phase<DEC_MAX_B>(sm, B, D, L.in_w, L.in_b, nullptr, 0, p.qkv, 3 * D, 3 * D, MMVID_ACT_NONE);
+    gemv_phase<DEC_MAX_B>(sm, B, D, L.in_w, L.in_b, nullptr, 0, p.qkv, 3 * D, 3 * D, MMVID_ACT_NONE, sm_part);
     grid.sync();
     // ---- phase 2: append K,V of the new token; split-KV single-query attention: item = (b, h, z) owns keys
     //      z*8 + warp, + 8Z, ... so that ALL blocks stream the cache (a (b,h)-per-block mapping leaves 2/3 of the SMs
@@ -416,20 +472,20 @@ __global__ void __launch_bounds__(256) artv_decode_persistent_kernel(DecodeParam
       sm[i] = O / Ls;
     }
     __syncthreads();
-    gemv_phase<DEC_MAX_B>(sm, B, D, L.out_w, L.out_b, p.h, D, p.h, D, D, MMVID_ACT_NONE);
+    gemv_phase<DEC_MAX_B>(sm, B, D, L.out_w, L.out_b, p.h, D, p.h, D, D, MMVID_ACT_NONE, sm_part);
     grid.sync();
     // ---- phase 4: mid = QuickGELU(LN2(h) W_fc^T + b)
     stage_rows(sm, p.h, B, D, L.ln2_w, L.ln2_b, red);
-    gemv_phase<DEC_MAX_B>(sm, B, D, L.fc_w, L.fc_b, nullptr, 0, p.mid, 4 * D, 4 * D, MMVID_ACT_QUICKGELU);
+    gemv_phase<DEC_MAX_B>(sm, B, D, L.fc_w, L.fc_b, nullptr, 0, p.mid, 4 * D, 4 * D, MMVID_ACT_QUICKGELU, sm_part);
     grid.sync();
     // ---- phase 5: h += mid W_proj^T + b
     stage_rows(sm, p.mid, B, 4 * D, nullptr, nullptr, red);
-    gemv_phase<DEC_MAX_B>(sm, B, 4 * D, L.proj_w, L.proj_b, p.h, D, p.h, D, D, MMVID_ACT_NONE);
+    gemv_phase<DEC_MAX_B>(sm, B, 4 * D, L.proj_w, L.proj_b, p.h, D, p.h, D, D, MMVID_ACT_NONE, sm_part);
     grid.sync();
   }
   if (p.head_w != nullptr) {
     stage_rows(sm, p.h, B, D, p.head_ln_w, p.head_ln_b, red);
-    gemv_phase<DEC_MAX_B>(sm, B, D, p.head_w, p.head_b, nullptr, 0, p.logits, p.n_logits, p.n_logits, MMVID_ACT_NONE);
+    gemv_phase<DEC_MAX_B>(sm, B, D, p.head_w, p.head_b, nullptr, 0, p.logits, p.n_logits, p.n_logits, MMVID_ACT_NONE, sm_part);
   }
 }
 

@@ -45,10 +45,16 @@ __device__ __forceinline__ void ffma2(float x0, float x1, float s, float b, floa
 }
 
 struct Att2Args {
+  unsigned long long* trace;  // debug timeline (mmvid_debug_attention_trace), normally null
   void* out; long long ldo; int out_bf16;
   int B, H, S, S_pad, mask_kind;
   int prev_rows[4]; int n_prev;
 };
+
+// CTA (0,0) stamps clock64() at pipeline events when a trace buffer is installed (scripts/att_trace.py)
+__device__ __forceinline__ void att2_stamp(const Att2Args& a, int idx) {
+  if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) a.trace[idx] = clock64();
+}
 
 template <bool TF32>
 constexpr size_t att2_smem_bytes() {
@@ -177,9 +183,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&p_ready[g], ph);                  // group g wrote P_j over S_g (and rescaled O_g if it had to)
           tc_fence_after();
+          if (j < 32) att2_stamp(a, j * 4 + g * 2);
           if (j == 0 && g == 0) issue_qk(1, 0);        // delayed start of tile B (see above)
           issue_pv(g, st, j == 0);
           if (more) issue_qk(g, st ^ 1);               // S_g is free: PV_j (same issue stream) consumed P_j first
+          if (j < 32) att2_stamp(a, j * 4 + g * 2 + 1);
         }
       }
       tc_commit(all_done);
@@ -212,10 +220,14 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
       const bool tile_full = __all_sync(0xffffffffu, (kv0 >= lo) && (kv0 + BKV <= hi));
       mbar_wait(&s_full[g], ph);
       tc_fence_after();
+      const bool tr = (qd == 0 && lane == 0 && j < 32);
+      const int tb = 128 + g * 192 + j * 6;
+      if (tr) att2_stamp(a, tb + 0);
       uint32_t r[4][32];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) tmem_ld32(t_s + ch * 32, r[ch]);
       tmem_ld_wait();
+      if (tr) att2_stamp(a, tb + 1);
       if (!tile_full) {
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
@@ -234,6 +246,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
           if (i + 3 < 32) mx1 = fmax3(mx1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
         }
       const float mx = fmaxf(mx0, mx1);
+      if (tr) att2_stamp(a, tb + 2);
       // move the reference only when needed (warp-uniform decision because TMEM ld/st are warp collectives)
       const bool need = (mx != -INFINITY) && (m_ref == -INFINITY || (mx - m_ref) * c > RESCALE_THRESH);
       float alpha = 1.f;
@@ -281,10 +294,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
         if constexpr (TF32) tmem_st32(t_s + ch * 32, r[ch]);
         else tmem_st16(t_s + ch * 16, pk);
       }
+      if (tr) att2_stamp(a, tb + 3);
       tmem_st_wait();
+      if (tr) att2_stamp(a, tb + 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[g]);  // one arrival per warp (4 per group), not 128 serialised ones
+      if (tr) att2_stamp(a, tb + 5);
       l += rs0 + rs1;
     }
     // every MMA of BOTH groups must have retired before K/V smem is recycled as the output staging area
@@ -319,7 +335,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention_tc2_kernel(const __
         }
       }
     } else {
-      constexpr int LD = HD + 4;
+      // tf32: two 32 KB K (V) tiles hold 128 x 68 floats; bf16 operands leave 2 x 16 KB = exactly 128 x 64 floats
+      // (fp32 output from the bf16 kernel is not a model path: unpadded rows, bank conflicts accepted)
+      constexpr int LD = TF32 ? HD + 4 : HD;
       float* st = reinterpret_cast<float*>(stage_base) + (size_t)row_local * LD;
 #pragma unroll
       for (int i = 0; i < HD; i += 4)
@@ -358,10 +376,21 @@ int launch_att2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 }  // namespace
 
 // called by mmvid_attention (tc_attention.cu) unless MMVID_ATT_IMPL=1 selects the one-tile kernel
+static unsigned long long* g_att2_trace = nullptr;
+// Debug / profiling hook: CTA (0,0) of every following attention launch writes clock64() stamps of its pipeline events
+// into `dev_buf` (>= 512 entries; pass NULL to switch it off).  MMA warp: [j*4 + g*2] p_ready_g observed,
+// [+1] PV_g(j) / QK_g(j+1) issued; softmax warp of tile g: [128 + g*192 + j*6 + {0: S ready, 1: S in registers,
+// 2: row max, 3: exps done / P stores issued, 4: P stores landed, 5: p_ready signalled}].
+extern "C" int mmvid_debug_attention_trace(unsigned long long* dev_buf) {
+  g_att2_trace = dev_buf;
+  return MMVID_OK;
+}
+
 extern "C" int mmvid_attention_v3(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
                                   int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
                                   const int* host_prev_rows, int n_prev, int tf32, cudaStream_t st) {
   Att2Args a{};
+  a.trace = g_att2_trace;
   a.out = out; a.ldo = ldo; a.out_bf16 = out_bf16;
   a.B = B; a.H = H; a.S = S; a.S_pad = S_pad; a.mask_kind = mask_kind; a.n_prev = n_prev;
   for (int i = 0; i < n_prev; ++i) a.prev_rows[i] = host_prev_rows[i];

@@ -1,5 +1,11 @@
 """Times one ART-V decode step (persistent cooperative kernel vs native per-layer launches) at fixed cache lengths."""
-import sys, ctypes as C, torch
+import argparse, sys, ctypes as C, torch
+ap = argparse.ArgumentParser()
+ap.add_argument("--impl", default="persistent,native")
+ap.add_argument("--pos", default="400,1300,2300")
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--warm", type=int, default=3)
+ARGS = ap.parse_args()
 sys.path.insert(0, ".")
 from mmvid_b200 import _lib as L, ops
 lib = L.load()
@@ -21,8 +27,8 @@ lnw, lnb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
 logits = torch.empty(B, 1024, device=dev)
 h0 = r(B, D) * 50
 st = ops._stream()
-for pos in (400, 1300, 2300):
-    for name in ("persistent", "native"):
+for pos in [int(x) for x in ARGS.pos.split(",")]:
+    for name in ARGS.impl.split(","):
         def call():
             h = h0.clone()
             if name == "persistent":
@@ -31,11 +37,11 @@ for pos in (400, 1300, 2300):
             else:
                 L.check(lib.mmvid_artv_decode_step(layers, NL, ops._ptr(h), ops._ptr(ws), B, D, H, S_max, pos, st))
             return h
-        for _ in range(3): call()
+        for _ in range(ARGS.warm): call()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(20): call()
+        for _ in range(ARGS.reps): call()
         e1.record(); torch.cuda.synchronize()
-        print(f"pos {pos} {name}: {e0.elapsed_time(e1) / 20 * 1000:.0f} us per step", flush=True)
+        print(f"pos {pos} {name}: {e0.elapsed_time(e1) / ARGS.reps * 1000:.0f} us per step", flush=True)
     a = None

@@ -61,15 +61,19 @@ def test_attention_fullsize_rows_are_convex_combinations(prec, kind):
     qkv_c = qkv.clone()
     qkv_c[:, 2 * D:] = const
     mk, rows = (MASK_NONE, []) if kind == "none" else (MASK_PREV, [65, 66])
-    out = ops.attention_tc(qkv_c, B, S, H, mk, rows, prec)
+    odt = torch.float32 if prec == "tf32" else torch.bfloat16   # the model's activation dtype of each mode
+    out = ops.attention_tc(qkv_c, B, S, H, mk, rows, prec, out_dtype=odt).float()
     tol = 2e-3 if prec == "tf32" else 1e-2
     assert (out - const).abs().max() < tol * const.abs().max()
     if kind == "none":
-        ref = ops.attention_tc(qkv, B, S, H, mk, rows, prec)
+        ref = ops.attention_tc(qkv, B, S, H, mk, rows, prec, out_dtype=odt).float()
         perm = torch.randperm(S, generator=g).cuda()
         q3 = qkv.view(B, S, 3 * D).clone()
         q3[:, :, D:] = q3[:, perm, D:]
-        out_p = ops.attention_tc(q3.view(B * S, 3 * D), B, S, H, mk, rows, prec)
+        out_p = ops.attention_tc(q3.view(B * S, 3 * D), B, S, H, mk, rows, prec, out_dtype=odt).float()
+        if prec == "bf16":   # fp32 output from the bf16 kernel (not a model path) must agree with its bf16 output
+            out32 = ops.attention_tc(qkv, B, S, H, mk, rows, prec, out_dtype=torch.float32)
+            assert relerr(out32, ref) < 5e-3
         assert relerr(out_p, ref) < (2e-3 if prec == "tf32" else 2e-2)
 
 
