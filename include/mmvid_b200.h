@@ -141,6 +141,13 @@ int mmvid_artv_decode_persistent(const mmvid_decode_layer* host_layers, int n_la
                                  const float* head_ln_w, const float* head_ln_b, const float* head_w,
                                  const float* head_b, float* logits, int n_logits, int B, int D, int H, int S_max,
                                  int pos, mmvid_stream_t stream);
+/* Same contract, third generation (decode_pdl.cu): 5 fused launches per layer (LayerNorm, cache append, split-KV
+ * combine, bias / QuickGELU / residual folded in) chained with programmatic dependent launch so that each kernel streams
+ * its weights from HBM while its predecessor is still running.  ws must be ZERO-INITIALISED once by the caller. */
+int mmvid_artv_decode_fused(const mmvid_decode_layer* host_layers, int n_layers, float* h, float* ws,
+                                 const float* head_ln_w, const float* head_ln_b, const float* head_w,
+                                 const float* head_b, float* logits, int n_logits, int B, int D, int H, int S_max,
+                                 int pos, mmvid_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K14  VQ nearest-codeword lookup (taming/modules/vqvae/quantize.py:302-311):

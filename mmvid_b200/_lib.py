@@ -59,6 +59,7 @@ SIGNATURES = {
     "mmvid_artv_decode_workspace_floats": (_ll, [_i, _i, _i]),
     "mmvid_artv_decode_step": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mmvid_artv_decode_persistent": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mmvid_artv_decode_fused": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mmvid_vq_argmin": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
     "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),

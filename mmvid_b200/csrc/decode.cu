@@ -237,7 +237,7 @@ extern "C" int mmvid_decode_attention(const float* q, long long q_bstride, const
 // ------------------------------------------------------------------------------------------------
 extern "C" long long mmvid_artv_decode_workspace_floats(int B, int D, int H) {
   const long long items = (long long)B * H * 16 > 4096 ? (long long)B * H * 16 : 4096;  // split-KV partial slots
-  return (long long)B * (D + 3 * D + D + 4 * D) + items * 66;
+  return (long long)B * (D + 3 * D + D + 4 * D) + items * 66 + 1024;  // + split-KV arrival counters (decode_pdl.cu)
 }
 
 extern "C" int mmvid_artv_decode_step(const mmvid_decode_layer* layers, int n_layers, float* h, float* ws, int B, int D,

@@ -63,6 +63,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Pure polling wait (mbarrier.test_wait never suspends the thread): a waiter woken out of try_wait's hardware suspend was
+// measured to observe the phase flip 220-440 cycles late in the attention pipeline (profiles/r1_g_*); use this on the
+// one or two waits that sit on a kernel's critical dependency loop, and plain mbar_wait everywhere else.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 28)) { asm volatile("trap;"); }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -288,11 +288,13 @@ class DALLE(nn.Module):
                 e.fc_w, e.fc_b = blk.mlp.c_fc.weight.data_ptr(), blk.mlp.c_fc.bias.data_ptr()
                 e.proj_w, e.proj_b = blk.mlp.c_proj.weight.data_ptr(), blk.mlp.c_proj.bias.data_ptr()
                 e.kcache, e.vcache = kc[li].data_ptr(), vc[li].data_ptr()
-            ws = torch.empty(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev, dtype=torch.float32)
+            ws = torch.zeros(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev, dtype=torch.float32)
             # 'native': 8 launches / layer issued from C (measured 0.88-1.06 ms / token at B = 4);
             # 'persistent': one cooperative launch per token with grid barriers (opt-in)
-            impl = os.environ.get("MMVID_ARTV_DECODE", getattr(self, "decode_impl", "native"))
+            # 'fused' (default, B <= 8): 5 launches / layer chained with programmatic dependent launch (decode_pdl.cu)
+            impl = os.environ.get("MMVID_ARTV_DECODE", getattr(self, "decode_impl", "fused"))
             persistent = impl == "persistent" and B <= 8 and len(blocks) <= 24
+            fused = impl == "fused" and B <= 8
             ln, lin = self.to_logits[0], self.to_logits[1]
             head_w = lin.weight.detach()[lo:lo + self.num_image_tokens]
             head_b = lin.bias.detach()[lo:lo + self.num_image_tokens]
@@ -318,6 +320,13 @@ class DALLE(nn.Module):
                                        pos=pos_table[t:t + 1])])
             h = xt.view(B, D)
             pos = P + t
+            if native and fused:
+                L.check(lib.mmvid_artv_decode_fused(layers, len(blocks), ops._ptr(h), ops._ptr(ws), ops._ptr(ln.weight),
+                                                    ops._ptr(ln.bias), ops._ptr(head_w), ops._ptr(head_b),
+                                                    ops._ptr(logits_buf), self.num_image_tokens, B, D, H, S_max, pos,
+                                                    ops._stream()), "artv_decode_fused")
+                logits = logits_buf
+                continue
             if native and persistent:
                 # ONE cooperative launch: 12 layers + LN + image-logit head, grid barriers between phases
                 L.check(lib.mmvid_artv_decode_persistent(layers, len(blocks), ops._ptr(h), ops._ptr(ws), ops._ptr(ln.weight),

@@ -1,7 +1,7 @@
 """Times one ART-V decode step (persistent cooperative kernel vs native per-layer launches) at fixed cache lengths."""
 import argparse, sys, ctypes as C, torch
 ap = argparse.ArgumentParser()
-ap.add_argument("--impl", default="persistent,native")
+ap.add_argument("--impl", default="fused,persistent,native")
 ap.add_argument("--pos", default="400,1300,2300")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--warm", type=int, default=3)
@@ -21,7 +21,7 @@ for li in range(NL):
              kcache=r(B, H, S_max, 64), vcache=r(B, H, S_max, 64))
     keep.append(t)
     for k, v in t.items(): setattr(layers[li], k, v.data_ptr())
-ws = torch.empty(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev)
+ws = torch.zeros(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev)
 head_w, head_b = r(1024, D), r(1024)
 lnw, lnb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
 logits = torch.empty(B, 1024, device=dev)
@@ -31,7 +31,10 @@ for pos in [int(x) for x in ARGS.pos.split(",")]:
     for name in ARGS.impl.split(","):
         def call():
             h = h0.clone()
-            if name == "persistent":
+            if name == "fused":
+                L.check(lib.mmvid_artv_decode_fused(layers, NL, ops._ptr(h), ops._ptr(ws), ops._ptr(lnw), ops._ptr(lnb), ops._ptr(head_w),
+                                                    ops._ptr(head_b), ops._ptr(logits), 1024, B, D, H, S_max, pos, st))
+            elif name == "persistent":
                 L.check(lib.mmvid_artv_decode_persistent(layers, NL, ops._ptr(h), ops._ptr(ws), ops._ptr(lnw), ops._ptr(lnb), ops._ptr(head_w),
                                                          ops._ptr(head_b), ops._ptr(logits), 1024, B, D, H, S_max, pos, st))
             else:
@@ -40,8 +43,12 @@ for pos in [int(x) for x in ARGS.pos.split(",")]:
         for _ in range(ARGS.warm): call()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import time
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(ARGS.reps): call()
+        t_cpu = (time.perf_counter() - t0) / ARGS.reps * 1e6
         e1.record(); torch.cuda.synchronize()
+        print(f"    (CPU enqueue {t_cpu:.0f} us per step)", end=" ")
         print(f"pos {pos} {name}: {e0.elapsed_time(e1) / ARGS.reps * 1000:.0f} us per step", flush=True)
     a = None

@@ -127,7 +127,7 @@ def test_bert_shapeA_generation_is_seeded_valid_and_decode_consistent():
     assert not torch.equal(s2, s0)
 
 
-@pytest.mark.parametrize("impl", ["native", "persistent"])
+@pytest.mark.parametrize("impl", ["fused", "native", "persistent"])
 def test_artv_shapeA_kv_cache_logits_match_full_causal_forward(impl):
     """ART-V at Shape A (prefix 321, 2048 decode steps, S = 2368): the per-step image logits produced from the KV cache
     equal the rows of ONE full causal forward over the generated sequence - which is what the reference recomputes from

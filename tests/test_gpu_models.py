@@ -187,7 +187,7 @@ def test_artv_forward_logits_vs_reference_golden(prec):
     assert float(logits[:, :spec.text_seq_len, spec.num_text_tokens:].max()) < -1e30
 
 
-@pytest.mark.parametrize("reps,impl", [(1, "native"), (1, "persistent"), (5, "native"), (9, "native")])
+@pytest.mark.parametrize("reps,impl", [(1, "fused"), (4, "fused"), (1, "native"), (1, "persistent"), (5, "native"), (9, "native")])
 def test_artv_kv_cache_generate_matches_no_cache_oracle_on_gpu(reps, impl):
     """B=2 through the native per-layer launches and through the persistent cooperative decode kernel; reps=5 -> B=10:
     native; reps=9 -> B=18: generic path.  All must reproduce the reference's full re-forward sampling bit for bit."""
