@@ -1,0 +1,82 @@
+// Profiling hook (not on the data path): raw tcgen05.mma issue rates of the instruction shapes the attention and GEMM
+// kernels use, measured with clock64() around n back-to-back MMAs + one commit on a single CTA.  Operand contents are
+// whatever is in shared / tensor memory (the rate does not depend on data).
+//   flavor 0: SS kind::tf32 128x128x8    (Q K^T, GEMM)       1: TS kind::tf32 128x64x8   (P V, A = P in TMEM)
+//          2: SS kind::f16  128x128x16                        3: TS kind::f16  128x64x16
+//          4: SS kind::tf32 128x256x8                         5: SS kind::f16  128x256x16
+//          6: attention pattern tf32: 16 x TS 128x64 then 8 x SS 128x128, repeated   7: same, kind::f16 (8 + 4)
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace mmvid;
+using namespace mmvid::tc;
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int flavor, int n_mma, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~(uintptr_t)1023);
+  for (int i = threadIdx.x; i < 98304 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tiles)[i] = 0;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_ptr;
+  if (warp == 0 && elect_one()) {
+    const uint64_t ad = make_smem_desc_sw128(smem_u32(tiles));
+    const uint64_t bd = make_smem_desc_sw128(smem_u32(tiles + 32768));
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t kk = (uint32_t)(i & 3) * 32;
+      switch (flavor) {
+        case 0: mma_ss<true>(tm, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<true>(128, 128), 1); break;
+        case 1: mma_ts<true>(tm + 384, tm + (i & 15) * 8, desc_advance(bd, kk), make_idesc<true>(128, 64), 1); break;
+        case 2: mma_ss<false>(tm, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<false>(128, 128), 1); break;
+        case 3: mma_ts<false>(tm + 384, tm + (i & 7) * 8, desc_advance(bd, kk), make_idesc<false>(128, 64), 1); break;
+        case 4: mma_ss<true>(tm, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<true>(128, 256), 1); break;
+        case 5: mma_ss<false>(tm, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<false>(128, 256), 1); break;
+        case 6: {
+          const int r = i % 24;
+          if (r < 16) mma_ts<true>(tm + 384, tm + r * 8, desc_advance(bd, kk), make_idesc<true>(128, 64), 1);
+          else mma_ss<true>(tm + 128, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<true>(128, 128), 1);
+          break;
+        }
+        default: {
+          const int r = i % 12;
+          if (r < 8) mma_ts<false>(tm + 384, tm + r * 8, desc_advance(bd, kk), make_idesc<false>(128, 64), 1);
+          else mma_ss<false>(tm + 128, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<false>(128, 128), 1);
+          break;
+        }
+      }
+    }
+    const long long t1 = clock64();
+    tc_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = (unsigned long long)(t1 - t0);  // issue time
+    out[1] = (unsigned long long)(t2 - t0);  // issue + execution of all n MMAs
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
+}  // namespace
+
+extern "C" int mmvid_debug_mma_rate(int flavor, int n_mma, unsigned long long* dev_out, mmvid_stream_t stream) {
+  MMVID_REQUIRE(flavor >= 0 && flavor <= 7 && n_mma > 0 && dev_out != nullptr, "flavor 0..7");
+  static bool attr_set = false;
+  const int smem = 98304 + 1024 + 256;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(mma_rate): %s", cudaGetErrorString(err));
+    attr_set = true;
+  }
+  mma_rate_kernel<<<1, 128, smem, to_stream(stream)>>>(flavor, n_mma, dev_out);
+  return check_launch("mma_rate");
+}

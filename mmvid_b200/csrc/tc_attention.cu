@@ -327,6 +327,21 @@ extern "C" int mmvid_attention_v3(const CUtensorMap* tq, const CUtensorMap* tk, 
                                   int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
                                   const int* host_prev_rows, int n_prev, int tf32, cudaStream_t st);
 
+extern "C" int mmvid_attention_v5(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
+                                  int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
+                                  const int* host_prev_rows, int n_prev, int tf32, int poly8, int spin, int dual,
+                                  int pingpong, unsigned long long* trace, cudaStream_t st);
+namespace mmvid { extern unsigned long long* g_att_trace; }
+
+namespace {
+constexpr int ATT_IMPL_DEFAULT = 2;
+constexpr int ATT_POLY_DEFAULT = 0;
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && v[0]) ? atoi(v) : dflt;
+}
+}  // namespace
+
 extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, void* out, int out_dtype, long long ldo,
                                int B, int H, int S, int S_pad, int mask_kind, const int* host_prev_rows, int n_prev,
                                int precision, mmvid_stream_t stream) {
@@ -355,9 +370,16 @@ extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, voi
     if (rc) return rc;
   }
   {
-    // default: two-tile ping-pong kernel (tc_attention2.cu); MMVID_ATT_IMPL=1 selects the one-tile kernel below
-    const char* impl = getenv("MMVID_ATT_IMPL");
-    if (!(impl && impl[0] == '1'))
+    // MMVID_ATT_IMPL: 3 = rotating-score-buffer kernel (tc_attention3.cu), 2 = two-tile ping-pong kernel
+    // (tc_attention2.cu), 1 = the one-tile kernel below.  MMVID_ATT_POLY (0|2|4 of every 8 exponentials on the FMA
+    // pipe) MMVID_ATT_SPIN (0|1) and MMVID_ATT_DUAL (0|1: one or two MMA-issuing threads) tune kernel 3.
+    const int impl = env_int("MMVID_ATT_IMPL", ATT_IMPL_DEFAULT);
+    if (impl == 3)
+      return mmvid_attention_v5(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind,
+                                host_prev_rows, n_prev, tf32 ? 1 : 0, env_int("MMVID_ATT_POLY", ATT_POLY_DEFAULT),
+                                env_int("MMVID_ATT_SPIN", 0), env_int("MMVID_ATT_DUAL", 1), env_int("MMVID_ATT_PP", 1),
+                                mmvid::g_att_trace, to_stream(stream));
+    if (impl != 1)
       return mmvid_attention_v3(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind,
                                 host_prev_rows, n_prev, tf32 ? 1 : 0, to_stream(stream));
   }

@@ -376,13 +376,13 @@ int launch_att2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 }  // namespace
 
 // called by mmvid_attention (tc_attention.cu) unless MMVID_ATT_IMPL=1 selects the one-tile kernel
-static unsigned long long* g_att2_trace = nullptr;
+namespace mmvid { unsigned long long* g_att_trace = nullptr; }
 // Debug / profiling hook: CTA (0,0) of every following attention launch writes clock64() stamps of its pipeline events
 // into `dev_buf` (>= 512 entries; pass NULL to switch it off).  MMA warp: [j*4 + g*2] p_ready_g observed,
 // [+1] PV_g(j) / QK_g(j+1) issued; softmax warp of tile g: [128 + g*192 + j*6 + {0: S ready, 1: S in registers,
 // 2: row max, 3: exps done / P stores issued, 4: P stores landed, 5: p_ready signalled}].
 extern "C" int mmvid_debug_attention_trace(unsigned long long* dev_buf) {
-  g_att2_trace = dev_buf;
+  mmvid::g_att_trace = dev_buf;
   return MMVID_OK;
 }
 
@@ -390,7 +390,7 @@ extern "C" int mmvid_attention_v3(const CUtensorMap* tq, const CUtensorMap* tk, 
                                   int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
                                   const int* host_prev_rows, int n_prev, int tf32, cudaStream_t st) {
   Att2Args a{};
-  a.trace = g_att2_trace;
+  a.trace = mmvid::g_att_trace;
   a.out = out; a.ldo = ldo; a.out_bf16 = out_bf16;
   a.B = B; a.H = H; a.S = S; a.S_pad = S_pad; a.mask_kind = mask_kind; a.n_prev = n_prev;
   for (int i = 0; i < n_prev; ++i) a.prev_rows[i] = host_prev_rows[i];

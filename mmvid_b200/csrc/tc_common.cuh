@@ -55,19 +55,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a broken pipeline traps (surfacing as a CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a broken pipeline traps (surfacing as a CUDA error) after ~2 s of wall time instead of hanging the GPU
+// box.  The bound is on time, not on the number of polls: one try_wait may suspend the thread for a long while.
+constexpr uint64_t MBAR_TIMEOUT_NS = 2000000000ull;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { asm volatile("trap;"); }
+    if (globaltimer_ns() - t0 > MBAR_TIMEOUT_NS) { asm volatile("trap;"); }
   }
 }
 
-// Pure polling wait (mbarrier.test_wait never suspends the thread): a waiter woken out of try_wait's hardware suspend was
-// measured to observe the phase flip 220-440 cycles late in the attention pipeline (profiles/r1_g_*); use this on the
-// one or two waits that sit on a kernel's critical dependency loop, and plain mbar_wait everywhere else.
+// Pure polling wait (mbarrier.test_wait never suspends the thread).  Measured (profiles/r1_f_attention_v5.md): no gain
+// over try_wait on the attention kernel's P(n) dependency; kept as a tuning switch.
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0, ok = 0;
+  uint64_t t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
@@ -77,7 +85,10 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (ok) break;
-    if (++spins > (1u << 28)) { asm volatile("trap;"); }
+    if ((++spins & 1023u) == 0) {
+      if (t0 == 0) t0 = globaltimer_ns();
+      else if (globaltimer_ns() - t0 > MBAR_TIMEOUT_NS) { asm volatile("trap;"); }
+    }
   }
 }
 

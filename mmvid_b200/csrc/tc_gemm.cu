@@ -78,6 +78,7 @@ struct EpiArgs {
   // QKV mode (qkv_q != nullptr): the [M, 3*H*64] result is scattered straight into the attention layout
   //   Q,K -> [B,H,S_pad,64]   V -> V^T [B,H,64,S_pad]   (fp32 or bf16 via c_bf16); bias applied, no act/residual
   void* qkv_q; void* qkv_k; void* qkv_vt; int qS, qSpad, qH;
+  int spin;    // 1: the TMA / MMA threads poll their ring barriers (mbar_wait_spin) instead of suspending in try_wait
   int raster;  // 0: m fastest; 1: n fastest; 2: 8-wide n groups (each wave covers ~8 weight tiles x ~18 row tiles)
 };
 
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          if (e.spin) mbar_wait_spin(&empty[s], ph ^ 1); else mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], STAGE_BYTES);
           uint8_t* a = tiles + s * STAGE_BYTES;
           if constexpr (CONV) {
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
+          if (e.spin) mbar_wait_spin(&full[s], ph); else mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
@@ -378,6 +379,7 @@ int num_sms() {
 
 // pick the N tile that minimises (#rounds over the SMs) x (tile width): larger tiles halve the L2->SM operand
 // traffic per FLOP, smaller ones quantise better on small problems
+constexpr int GEMM_SPIN_DEFAULT = 0;
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -413,6 +415,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream
   }
   e.num_m_tiles = (int)ceil_div<long long>(e.M, BM);
   e.num_n_tiles = ceil_div(e.N, BN);
+  e.spin = env_int("MMVID_GEMM_SPIN", GEMM_SPIN_DEFAULT);
   e.raster = env_int("MMVID_GEMM_RASTER", 1);  // n fastest: consecutive CTAs share the activation tile (measured best)
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());

@@ -27,6 +27,7 @@ struct Epi2Args {
   void* C; long long ldc; int c_bf16;
   long long M; int N, K, act;
   int num_m_tiles /* 256-row tiles */, num_n_tiles;
+  int spin;  // 1: TMA / MMA threads poll their ring barriers (see tc_gemm.cu)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -139,7 +140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          if (e.spin) mbar_wait_spin(&empty[s], ph ^ 1); else mbar_wait(&empty[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);  // bytes landing in BOTH CTAs
           const uint32_t full_leader = mapa_u32(smem_u32(&full[s]), 0);
           uint8_t* a = tiles + s * STAGE_BYTES;
@@ -160,7 +161,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
+          if (e.spin) mbar_wait_spin(&full[s], ph); else mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
@@ -325,6 +326,7 @@ extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const
   Epi2Args e{};
   e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc; e.c_bf16 = c_dtype == MMVID_DT_BF16;
   e.M = M; e.N = N; e.K = K; e.act = act;
+  { const char* v = getenv("MMVID_GEMM_SPIN"); e.spin = v ? atoi(v) : 0; }
   if (BN == 256) return tf32 ? launch2<true, 256>(tmA, tmB, e, st) : launch2<false, 256>(tmA, tmB, e, st);
   return tf32 ? launch2<true, 128>(tmA, tmB, e, st) : launch2<false, 128>(tmA, tmB, e, st);
 }

@@ -1,0 +1,37 @@
+"""Timeline of CTA (0,0) of the rotating-score-buffer attention kernel (MMVID_ATT_IMPL=3) at the benchmark shape, plus the
+raw tcgen05.mma rates (mmvid_debug_mma_rate).  clock64 stamps relative to the first one."""
+import os, sys, ctypes as C
+os.environ.setdefault("MMVID_ATT_IMPL", "3")
+import torch
+sys.path.insert(0, ".")
+from mmvid_b200 import _lib as L, ops
+from mmvid_b200._lib import MASK_PREV
+lib = L.load()
+prec = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+out = torch.zeros(2, dtype=torch.int64, device="cuda")
+names = ["SS tf32 128x128x8", "TS tf32 128x64x8", "SS f16 128x128x16", "TS f16 128x64x16", "SS tf32 128x256x8", "SS f16 128x256x16",
+         "att pattern tf32 (16 TS + 8 SS)", "att pattern f16 (8 TS + 4 SS)"]
+for fl in range(8):
+    n = 960
+    for _ in range(2):
+        L.check(lib.mmvid_debug_mma_rate(fl, n, out.data_ptr(), None))
+        torch.cuda.synchronize()
+    t = out.cpu().tolist()
+    print(f"MMA {names[fl]:34s}: issue {t[0] / n:6.1f} clk/mma, total {t[1] / n:6.1f} clk/mma")
+B, S, H, D = 4, 2115, 12, 768
+qkv = torch.randn(B * S, 3 * D, device="cuda")
+odt = torch.float32 if prec == "tf32" else torch.bfloat16
+for _ in range(2):
+    ops.attention_tc(qkv, B, S, H, MASK_PREV, [65, 66], prec, out_dtype=odt)
+buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+L.check(lib.mmvid_debug_attention_trace(buf.data_ptr()))
+ops.attention_tc(qkv, B, S, H, MASK_PREV, [65, 66], prec, out_dtype=odt)
+torch.cuda.synchronize()
+L.check(lib.mmvid_debug_attention_trace(None))
+t = buf.cpu().tolist()
+t0 = min(x for x in t if x > 0)
+print(f"{prec} impl 3 poly {os.environ.get('MMVID_ATT_POLY', '0')}: n = 2j+g; MMA: P(n) seen, PV(n)+QK(n+3) issued | softmax g(n) step j: S ready, regs, max, exps, st landed, signalled")
+for n in range(0, 34):
+    j, g = n >> 1, n & 1
+    sm = [t[128 + g * 192 + j * 6 + i] - t0 for i in range(6)]
+    print(f"n={n:2d} (j={j:2d} {'AB'[g]}) MMA seen {t[2 * n] - t0:6d} issued {t[2 * n + 1] - t0:6d} | softmax {sm}  busy {sm[5] - sm[0]}")

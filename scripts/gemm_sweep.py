@@ -28,6 +28,11 @@ for (M,N,K,name) in json.loads(sys.argv[2]):
 print(json.dumps(res))
 '''
 QUICK = "--quick" in sys.argv
+if "--child" in sys.argv:   # one configuration in THIS process' environment: gemm_sweep.py --child <prec>
+    prec = sys.argv[sys.argv.index("--child") + 1]
+    r = subprocess.run([sys.executable, "-c", CHILD, prec, json.dumps(SHAPES)], capture_output=True, text=True, timeout=300)
+    print(prec, r.stdout.strip() or r.stderr[-800:], flush=True)
+    sys.exit(0)
 if "--2cta" in sys.argv:
     for prec in ("tf32", "bf16"):
         for bn2 in (0, 128, 256):
