@@ -234,6 +234,10 @@ int mmvid_transpose2d(const float* in, float* out, int R, int C, mmvid_stream_t 
  * stamps of its pipeline events into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/att_trace.py. */
 int mmvid_debug_attention_trace(unsigned long long* dev_buf);
 
+/* Profiling hook: CTA 0 of every following single-CTA tensor-core GEMM (mmvid_linear in TF32 / BF16 precision) writes
+ * clock64() stamps of its first 8 tiles into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/gemm_trace.py. */
+int mmvid_debug_gemm_trace(unsigned long long* dev_buf);
+
 /* Profiling hook: clock64() cost of n_mma back-to-back tcgen05.mma of one shape on one SM (flavors: see
  * csrc/debug_mma_rate.cu); dev_out[0] = issue cycles, dev_out[1] = cycles until the commit barrier fires. */
 int mmvid_debug_mma_rate(int flavor, int n_mma, unsigned long long* dev_out, mmvid_stream_t stream);

@@ -334,8 +334,7 @@ extern "C" int mmvid_attention_v5(const CUtensorMap* tq, const CUtensorMap* tk, 
 namespace mmvid { extern unsigned long long* g_att_trace; }
 
 namespace {
-constexpr int ATT_IMPL_DEFAULT = 2;
-constexpr int ATT_POLY_DEFAULT = 0;
+constexpr int ATT_IMPL_DEFAULT = 3;
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && v[0]) ? atoi(v) : dflt;
@@ -370,14 +369,15 @@ extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, voi
     if (rc) return rc;
   }
   {
-    // MMVID_ATT_IMPL: 3 = rotating-score-buffer kernel (tc_attention3.cu), 2 = two-tile ping-pong kernel
-    // (tc_attention2.cu), 1 = the one-tile kernel below.  MMVID_ATT_POLY (0|2|4 of every 8 exponentials on the FMA
-    // pipe) MMVID_ATT_SPIN (0|1) and MMVID_ATT_DUAL (0|1: one or two MMA-issuing threads) tune kernel 3.
+    // MMVID_ATT_IMPL: 3 (default) = rotating-score-buffer kernel (tc_attention3.cu), 2 = two-tile ping-pong kernel
+    // (tc_attention2.cu), 1 = the one-tile kernel below.  Measured defaults (profiles/r1_f_attention_v5.md): tf32 keeps
+    // every exponential on MUFU, bf16 moves 2 of 8 to the FMA pipe.  MMVID_ATT_POLY (0|2|4 of every 8 exponentials on the
+    // FMA pipe), MMVID_ATT_PP (0|1 MUFU ping-pong token) MMVID_ATT_SPIN (0|1) and MMVID_ATT_DUAL (0|1: one or two MMA-issuing threads) tune kernel 3.
     const int impl = env_int("MMVID_ATT_IMPL", ATT_IMPL_DEFAULT);
     if (impl == 3)
       return mmvid_attention_v5(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind,
-                                host_prev_rows, n_prev, tf32 ? 1 : 0, env_int("MMVID_ATT_POLY", ATT_POLY_DEFAULT),
-                                env_int("MMVID_ATT_SPIN", 0), env_int("MMVID_ATT_DUAL", 1), env_int("MMVID_ATT_PP", 1),
+                                host_prev_rows, n_prev, tf32 ? 1 : 0, env_int("MMVID_ATT_POLY", tf32 ? 0 : 2),
+                                env_int("MMVID_ATT_SPIN", 0), env_int("MMVID_ATT_DUAL", 1), env_int("MMVID_ATT_PP", 0),
                                 mmvid::g_att_trace, to_stream(stream));
     if (impl != 1)
       return mmvid_attention_v3(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind,

@@ -34,6 +34,7 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+constexpr int DT_F32_EXACT = 100;
 int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   PFN_encodeTiled fn = get_encode_fn();
@@ -46,7 +47,9 @@ int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, con
     es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  const CUtensorMapDataType dt = dtype == MMVID_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  // loads of fp32 operands use TFLOAT32 (round-to-nearest in the TMA unit); DT_F32_EXACT is for stores of fp32 results
+  const CUtensorMapDataType dt = dtype == MMVID_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (dtype == DT_F32_EXACT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MMVID_ECUDA, "cuTensorMapEncodeTiled failed (%s) code %lld", "", (long long)r);
@@ -78,6 +81,8 @@ struct EpiArgs {
   // QKV mode (qkv_q != nullptr): the [M, 3*H*64] result is scattered straight into the attention layout
   //   Q,K -> [B,H,S_pad,64]   V -> V^T [B,H,64,S_pad]   (fp32 or bf16 via c_bf16); bias applied, no act/residual
   void* qkv_q; void* qkv_k; void* qkv_vt; int qS, qSpad, qH;
+  int tma_store;  // 1: fp32 result tiles leave through TMA bulk stores (tmC), see the epilogue
+  unsigned long long* trace;  // debug timeline of CTA 0 (mmvid_debug_gemm_trace), normally null
   int spin;    // 1: the TMA / MMA threads poll their ring barriers (mbar_wait_spin) instead of suspending in try_wait
   int raster;  // 0: m fastest; 1: n fastest; 2: 8-wide n groups (each wave covers ~8 weight tiles x ~18 row tiles)
 };
@@ -97,6 +102,14 @@ __device__ __forceinline__ void tile_coords(const EpiArgs& e, int tile, int& mt,
   }
 }
 
+// CTA 0 stamps clock64() at pipeline events of its first 8 tiles when a trace buffer is installed (scripts/gemm_trace.py):
+// [t*64 + 0] MMA: accumulator free, [+1] first k-block landed, [+2] last k-block landed, [+3] tile committed,
+// [+8] epilogue warp 2: accumulator complete, [+9] accumulator in registers, [+10] tile stored,
+// [+16] TMA: first k-block issued, [+17] last k-block issued, [+24 + kb] MMA: k-block kb landed (kb < 32)
+__device__ __forceinline__ void gemm_stamp(const EpiArgs& e, uint32_t tile_iter, int idx) {
+  if (e.trace != nullptr && blockIdx.x == 0 && tile_iter < 8) e.trace[tile_iter * 64 + idx] = clock64();
+}
+
 template <int BN>
 constexpr int gemm_stages() { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
 
@@ -110,7 +123,8 @@ constexpr size_t gemm_smem_bytes() {
 // tile in L2).  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue), tile loop.
 template <bool TF32, int BN, bool CONV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                 const __grid_constant__ CUtensorMap tmB, EpiArgs e) {
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const __grid_constant__ CUtensorMap tmC, EpiArgs e) {
   constexpr int STAGES = gemm_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
   // carve: [barriers 256 B][pad to 1024][stages: A | B][epilogue staging]
@@ -147,8 +161,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   if (warp == 0) {
     if (elect_one()) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t it = 0, tma_tile = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tma_tile) {
         int mt, nt;
         tile_coords(e, tile, mt, nt);
         const int m0 = mt * BM, n0 = nt * BN;
@@ -174,6 +188,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             tma_load_2d(a, &tmA, &full[s], kb * BKE, m0);
           }
           tma_load_2d(a + A_BYTES, &tmB, &full[s], kb * BKE, n0);
+          if (kb == 0) gemm_stamp(e, tma_tile, 16);
+          if (kb == num_k - 1) gemm_stamp(e, tma_tile, 17);
         }
       }
     }
@@ -185,12 +201,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
+        gemm_stamp(e, tile_iter, 0);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           if (e.spin) mbar_wait_spin(&full[s], ph); else mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (e.trace != nullptr) {
+            if (kb == 0) gemm_stamp(e, tile_iter, 1);
+            if (kb == num_k - 1) gemm_stamp(e, tile_iter, 2);
+            if (kb < 32) gemm_stamp(e, tile_iter, 24 + kb);
+          }
           const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_BYTES);
@@ -201,6 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
         }
         tc_commit(&tmem_full[acc]);  // accumulator complete
+        gemm_stamp(e, tile_iter, 3);
       }
     }
   } else {
@@ -208,6 +231,104 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;
     const int ew = warp - 2;              // 0..7
     const int chalf = ew >> 2;            // which half of the tile's 32-column chunks this warp drains
+    if (e.tma_store) {
+      // ---- TMA-store epilogue (fp32 result, N % 32 == 0, 16-byte aligned rows).  The r1p source-level profile showed the
+      // transposing epilogue below to be INSTRUCTION bound: ~700 warp instructions per 32-column chunk (per-row
+      // predicates, 64-bit address arithmetic, shared-memory round trip), ~2900 clk per chunk, which caps the kernel as
+      // soon as the main loop gets faster (256-wide tiles).  Here a lane keeps its own output row: bias / activation /
+      // residual are applied in registers, the 32 x 32 chunk is written once to shared memory in the SWIZZLE_128B
+      // layout and one elected lane hands it to the TMA unit, which also clips the M tail.
+      const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 4096);
+      const uint32_t st_row = st_base + (uint32_t)(lane * 128);
+      constexpr int NCH = BN / 64;
+      constexpr int GRP = NCH < 2 ? NCH : 2;  // 64-wide tiles: one chunk per warp
+      if (lane == 0) prefetch_tmap(&tmC);
+      uint32_t tile_iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        int mt, nt;
+        tile_coords(e, tile, mt, nt);
+        const int m0 = mt * BM, n0 = nt * BN + chalf * (BN / 2);
+        const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+        const long long m_row = (long long)m0 + q * 32 + lane;   // the output row this lane owns
+        const bool row_ok = m_row < e.M;
+        // residual of the first chunk pair is requested before the accumulator wait (latency off the critical path)
+        float4 res[GRP][8];
+        auto load_res = [&](int c0) {
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc) {
+            const int ncol = n0 + (c0 + cc) * 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              res[cc][i] = (row_ok && ncol < e.N) ? *reinterpret_cast<const float4*>(e.residual + m_row * e.ldr + ncol + 4 * i)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        if (e.residual) load_res(0);
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+        const bool etr = (warp == 2 && lane == 0);
+        if (etr) gemm_stamp(e, tile_iter, 8);
+        const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < NCH; c0 += GRP) {
+          uint32_t racc[GRP][32];
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc) tmem_ld32(t_src + (c0 + cc) * 32, racc[cc]);
+          tmem_ld_wait();
+          if (c0 + GRP >= NCH) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (etr) gemm_stamp(e, tile_iter, 9);
+          }
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc) {
+            const int ncol = n0 + (c0 + cc) * 32;
+            if (ncol >= e.N) continue;  // warp-uniform
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + 4 * i));  // same address in every lane
+              o[4 * i + 0] = __uint_as_float(racc[cc][4 * i + 0]) + b.x;
+              o[4 * i + 1] = __uint_as_float(racc[cc][4 * i + 1]) + b.y;
+              o[4 * i + 2] = __uint_as_float(racc[cc][4 * i + 2]) + b.z;
+              o[4 * i + 3] = __uint_as_float(racc[cc][4 * i + 3]) + b.w;
+            }
+            if (e.act != MMVID_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = apply_act_fast(o[i], e.act);
+            }
+            if (e.residual) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                o[4 * i + 0] += res[cc][i].x; o[4 * i + 1] += res[cc][i].y;
+                o[4 * i + 2] += res[cc][i].z; o[4 * i + 3] += res[cc][i].w;
+              }
+            }
+            // the previous chunk's bulk store must have finished READING the staging buffer
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)  // 16-byte unit j of row r lives at unit j ^ (r & 7): the TMA 128-byte swizzle
+              sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(st_base), "r"(ncol), "r"(m0 + q * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (e.residual && c0 + GRP < NCH) load_res(c0 + GRP);
+        }
+        if (etr) gemm_stamp(e, tile_iter, 10);
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores done before smem goes away
+      __syncwarp();
+    } else {
     const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
     const uint32_t st_wr = st_base + (uint32_t)(lane * EPI_LD * 4);                       // my row while transposing
     const int col = (lane & 7) * 4, rsub = lane >> 3;                                     // coalesced phase mapping
@@ -240,22 +361,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
+      const bool etr = (warp == 2 && lane == 0);
+      if (etr) gemm_stamp(e, tile_iter, 8);
       const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
       const long long m_first = (long long)m0 + q * 32 + rsub;
-      // all of this warp's accumulator columns are requested back to back and awaited ONCE (a tcgen05.wait::ld per
-      // chunk costs a few hundred cycles of exposed latency)
-      uint32_t racc[NCH][32];
+      // this warp's accumulator columns are requested two 32-column chunks at a time and awaited once per pair (a
+      // tcgen05.wait::ld per chunk exposes a few hundred cycles each; more than two chunks in flight would not fit the
+      // register budget of the 256-wide tile)
+      constexpr int GRP = NCH < 2 ? NCH : 2;  // 64-wide tiles: one chunk per warp
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld32(t_src + c * 32, racc[c]);
+      for (int c0 = 0; c0 < NCH; c0 += GRP) {
+      uint32_t racc[GRP][32];
+#pragma unroll
+      for (int cc = 0; cc < GRP; ++cc) tmem_ld32(t_src + (c0 + cc) * 32, racc[cc]);
       tmem_ld_wait();
-      // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (c0 + GRP >= NCH) {
+        // the whole accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (etr) gemm_stamp(e, tile_iter, 9);
+      }
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (n0 + c * 32 >= e.N) break;
-        uint32_t (&r)[32] = racc[c];
+      for (int cc = 0; cc < GRP; ++cc) {
+        const int c = c0 + cc;
+        if (n0 + c * 32 >= e.N) continue;
+        uint32_t (&r)[32] = racc[cc];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           sts128(st_wr + (uint32_t)(((j ^ (lane & 7)) * 16)), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -356,7 +487,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         __syncwarp();
       }
+      }
+      if (etr) gemm_stamp(e, tile_iter, 10);
     }
+    }  // !tma_store
   }
   tc_fence_before();
   __syncthreads();
@@ -380,24 +514,30 @@ int num_sms() {
 // pick the N tile that minimises (#rounds over the SMs) x (tile width): larger tiles halve the L2->SM operand
 // traffic per FLOP, smaller ones quantise better on small problems
 constexpr int GEMM_SPIN_DEFAULT = 0;
+constexpr int GEMM_TMA_STORE_DEFAULT = 1;
+unsigned long long* g_gemm_trace = nullptr;
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 
-int pick_bn(long long M, int N) {
+int pick_bn(long long M, int N, bool allow256 = true) {
   const int forced = env_int("MMVID_GEMM_BN", 0);  // tuning / experiments only
   if (forced == 64 || forced == 128 || forced == 256) return forced;
   const int sms = num_sms();
   const long long mt = ceil_div<long long>(M, BM);
   int best = 64;
   double best_cost = 1e30;
-  const int cands[2] = {128, 64};  // 256-wide tiles lose: the epilogue (not the operand traffic) bounds short-K GEMMs
-  for (int i = 0; i < 2; ++i) {
+  // Per-tile cost in units of 128x128-tile k-loops, from the r1q / r1r pipeline traces: the 128-wide SS MMA is operand-fetch
+  // bound (380 clk per k-block instead of 256), the 256-wide one runs at the nominal 512 but has a 4-stage ring, so a
+  // 256-wide tile costs ~1.5x a 128-wide one for 2x the work; 64-wide tiles pay the same operand traffic as 128-wide ones.
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
+    if (bn == 256 && (N < 256 || !allow256)) continue;
     const long long tiles = mt * ceil_div(N, bn);
     const double rounds = (double)ceil_div<long long>(tiles, sms);
-    const double per_tile = bn + (bn == 64 ? 24 : (bn == 128 ? 12 : 0));  // small tiles pay more L2 traffic / overhead
+    const double per_tile = bn == 256 ? 212.0 : (bn == 128 ? 140.0 : 88.0);
     const double cost = rounds * per_tile;
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
@@ -416,10 +556,24 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream
   e.num_m_tiles = (int)ceil_div<long long>(e.M, BM);
   e.num_n_tiles = ceil_div(e.N, BN);
   e.spin = env_int("MMVID_GEMM_SPIN", GEMM_SPIN_DEFAULT);
+  e.trace = g_gemm_trace;
   e.raster = env_int("MMVID_GEMM_RASTER", 1);  // n fastest: consecutive CTAs share the activation tile (measured best)
+  // result tiles leave through TMA bulk stores when the output is plain row-major fp32 with 32-column granularity
+  CUtensorMap tmC = tmA;  // placeholder when unused
+  e.tma_store = 0;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (env_int("MMVID_GEMM_TMA_STORE", GEMM_TMA_STORE_DEFAULT) && !e.c_bf16 && e.qkv_q == nullptr && e.N % 32 == 0 &&
+      e.ldc % 4 == 0 && al16(e.C) && (!e.residual || (e.ldr % 4 == 0 && al16(e.residual))) && (!e.bias || al16(e.bias))) {
+    uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
+    uint64_t str[1] = {(uint64_t)e.ldc * 4};
+    uint32_t box[2] = {32, 32};
+    int rc = make_tensor_map(&tmC, e.C, DT_F32_EXACT, 2, dims, str, box);
+    if (rc) return rc;
+    e.tma_store = 1;
+  }
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  gemm_tc_kernel<TF32, BN, CONV><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, e);
+  gemm_tc_kernel<TF32, BN, CONV><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, e);
   return check_launch("gemm_tc");
 }
 
@@ -431,6 +585,13 @@ int launch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiA
 }
 
 }  // namespace
+
+// Debug / profiling hook: CTA 0 of every following single-CTA tensor-core GEMM launch writes clock64() stamps of its
+// first 8 tiles into dev_buf (>= 512 entries; NULL switches it off).  Layout: gemm_stamp above.
+extern "C" int mmvid_debug_gemm_trace(unsigned long long* dev_buf) {
+  g_gemm_trace = dev_buf;
+  return MMVID_OK;
+}
 
 extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
                                 const float* bias, const float* residual, long long ldr, void* C, int c_dtype,
@@ -464,7 +625,7 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
       return mmvid_linear_tc2(A, a_dtype, lda, W, w_dtype, ldw, bias, residual, ldr, C, c_dtype, ldc, M, N, K, act, precision,
                               bn2, st);
   }
-  const int BN = pick_bn(M, N);
+  const int BN = pick_bn(M, N, tf32);  // 256-wide tiles only pay in tf32 (r1s: bf16 c_fc 56 -> 68 us with them)
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
