@@ -248,6 +248,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 PFN_encodeTiled get_encode_fn();
 
+// dtype code for make_tensor_map: fp32 elements moved bit-exactly (result stores); MMVID_DT_F32 maps to TFLOAT32, which
+// rounds to tf32 in the TMA unit and is meant for operand loads only
+constexpr int DT_F32_EXACT = 100;
+
 // rank-`rank` tensor map, innermost dimension first.  strides_bytes has rank-1 entries (dims 1..rank-1).
 int make_tensor_map(CUtensorMap* out, const void* base, int dtype /*MMVID_DT_*/, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);

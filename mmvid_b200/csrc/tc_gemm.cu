@@ -34,7 +34,6 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-constexpr int DT_F32_EXACT = 100;
 int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   PFN_encodeTiled fn = get_encode_fn();
@@ -515,7 +514,10 @@ int num_sms() {
 // traffic per FLOP, smaller ones quantise better on small problems
 constexpr int GEMM_SPIN_DEFAULT = 0;
 constexpr int GEMM_TMA_STORE_DEFAULT = 1;
-unsigned long long* g_gemm_trace = nullptr;
+}  // namespace
+namespace mmvid { unsigned long long* g_gemm_trace = nullptr; }
+namespace {
+using mmvid::g_gemm_trace;
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -620,8 +622,23 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
     // single-CTA tile; short-K GEMMs are bounded by their output stream and gain nothing).  MMVID_GEMM_2CTA=128|256
     // forces it everywhere, =1 disables it.
     int bn2 = env_int("MMVID_GEMM_2CTA", 0);
+    if (bn2 == 0 && c_dtype == MMVID_DT_F32 && N >= 512 && M >= 1024) {
+      // An SS tcgen05.mma costs ~100 clk whatever its N (r1q-r1v traces: 380-430 clk per 4-instruction k-block for N = 128,
+      // 192 and 256 alike; the 128-row A slice fetch from shared memory is the floor), so only instructions with >= 100 clk
+      // of work run the tensor pipe at its rate: 256 x 192 / 256 x 256 CTA-pair tiles.  With the TMA-store epilogue these
+      // tiles are no longer epilogue bound (c_fc 80 -> 72 us, c_proj 72 -> 67 us).  Per-tile costs in k clk from the traces.
+      const int sms = num_sms();
+      const long long mt = ceil_div<long long>(M, BM), mt2 = ceil_div<long long>(M, 2 * BM);
+      const double c128 = (double)ceil_div<long long>(mt * ceil_div(N, 128), sms) * 11.2;
+      const double c256 = tf32 ? (double)ceil_div<long long>(mt * ceil_div(N, 256), sms) * 17.1 : 1e30;
+      const double p192 = (double)ceil_div<long long>(mt2 * ceil_div(N, 192), sms / 2) * 11.8;
+      const double p256 = (double)ceil_div<long long>(mt2 * ceil_div(N, 256), sms / 2) * 13.2;
+      const double best1 = c128 < c256 ? c128 : c256;
+      if (p256 <= p192 && p256 < best1) bn2 = 256;
+      else if (p192 < p256 && p192 < best1) bn2 = 192;
+    }
     if (bn2 == 0 && K >= 2048 && M >= 1024 && N >= 256) bn2 = 128;
-    if ((bn2 == 128 || bn2 == 256) && g_qkv.q == nullptr)
+    if ((bn2 == 128 || bn2 == 192 || bn2 == 256) && g_qkv.q == nullptr)
       return mmvid_linear_tc2(A, a_dtype, lda, W, w_dtype, ldw, bias, residual, ldr, C, c_dtype, ldc, M, N, K, act, precision,
                               bn2, st);
   }

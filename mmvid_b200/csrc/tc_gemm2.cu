@@ -15,6 +15,8 @@
 using namespace mmvid;
 using namespace mmvid::tc;
 
+namespace mmvid { extern unsigned long long* g_gemm_trace; }
+
 namespace {
 
 constexpr int BM = 128;  // rows per CTA (256 per pair)
@@ -28,7 +30,13 @@ struct Epi2Args {
   long long M; int N, K, act;
   int num_m_tiles /* 256-row tiles */, num_n_tiles;
   int spin;  // 1: TMA / MMA threads poll their ring barriers (see tc_gemm.cu)
+  int tma_store;  // 1: fp32 result tiles leave through TMA bulk stores (same epilogue as tc_gemm.cu)
+  unsigned long long* trace;  // debug timeline of cluster 0's leader CTA (same layout as gemm_stamp in tc_gemm.cu)
 };
+
+__device__ __forceinline__ void g2_stamp(const Epi2Args& e, uint32_t tile_iter, int idx) {
+  if (e.trace != nullptr && blockIdx.x == 0 && tile_iter < 8) e.trace[tile_iter * 64 + idx] = clock64();
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -86,7 +94,10 @@ __device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64
 }
 
 template <int BN>
-constexpr int g2_stages() { return BN == 256 ? 6 : 8; }
+constexpr int g2_stages() { return BN == 256 ? 6 : (BN == 192 ? 6 : 8); }
+// TMEM columns to allocate for two BN-wide accumulators (the allocator wants a power of two)
+template <int BN>
+constexpr int g2_tmem_cols() { return 2 * BN <= 256 ? 256 : 512; }
 template <int BN>
 constexpr size_t g2_smem_bytes() {
   return (size_t)g2_stages<BN>() * (BM * 128 + (BN / 2) * 128) + EPI_WARPS * 32 * EPI_LD * 4 + 1024 + 256;
@@ -94,7 +105,8 @@ constexpr size_t g2_smem_bytes() {
 
 template <bool TF32, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epi2Args e) {
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, Epi2Args e) {
   constexpr int STAGES = g2_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -122,7 +134,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc2(tmem_ptr, 2 * BN);
+    tmem_alloc2(tmem_ptr, g2_tmem_cols<BN>());
     tmem_relinquish2();
   }
   tc_fence_before();
@@ -157,12 +169,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
+        g2_stamp(e, tile_iter, 0);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           if (e.spin) mbar_wait_spin(&full[s], ph); else mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (e.trace != nullptr) {
+            if (kb == 0) g2_stamp(e, tile_iter, 1);
+            if (kb == num_k - 1) g2_stamp(e, tile_iter, 2);
+            if (kb < 32) g2_stamp(e, tile_iter, 24 + kb);
+          }
           const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_BYTES);
@@ -172,18 +190,113 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
           tc_commit2(&empty[s]);
         }
         tc_commit2(&tmem_full[acc]);
+        g2_stamp(e, tile_iter, 3);
       }
     }
   } else {
     const int q = warp & 3;
     const int ew = warp - 2;
     const int chalf = ew >> 2;
+    if (e.tma_store) {
+      // ---- TMA-store epilogue (see tc_gemm.cu): a lane keeps its own output row, bias / activation / residual are applied
+      // in registers, each 32 x 32 chunk goes to shared memory once (SWIZZLE_128B layout) and leaves as one bulk store.
+      // The r1t trace showed the transposing epilogue below to take 17 k clk per 128 x 256 tile against a 10.7 k clk main
+      // loop: the 256-wide CTA-pair tile was epilogue bound by a wide margin.
+      const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 4096);
+      const uint32_t st_row = st_base + (uint32_t)(lane * 128);
+      constexpr int NCH = BN / 64;  // 32-column chunks per warp (half of the tile); 3 for the 192-wide tile
+      constexpr int GRP = NCH < 2 ? NCH : 2;
+      if (lane == 0) prefetch_tmap(&tmC);
+      uint32_t tile_iter = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
+        const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
+        const int m0 = mt * (2 * BM) + (int)rank * BM, n0 = nt * BN + chalf * (BN / 2);
+        const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+        const long long m_row = (long long)m0 + q * 32 + lane;
+        const bool row_ok = m_row < e.M;
+        float4 res[GRP][8];
+        auto load_res = [&](int c0) {
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc) {
+            const int ncol = n0 + (c0 + cc) * 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              res[cc][i] = (row_ok && c0 + cc < NCH && ncol < e.N) ? *reinterpret_cast<const float4*>(e.residual + m_row * e.ldr + ncol + 4 * i)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        if (e.residual) load_res(0);
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+        const bool etr = (warp == 2 && lane == 0);
+        if (etr) g2_stamp(e, tile_iter, 8);
+        const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < NCH; c0 += GRP) {
+          uint32_t racc[GRP][32];
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc)
+            if (c0 + cc < NCH) tmem_ld32(t_src + (c0 + cc) * 32, racc[cc]);
+          tmem_ld_wait();
+          if (c0 + GRP >= NCH) {  // the whole accumulator is in registers: release it (leader's barrier, 16 arrivals)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+            if (etr) g2_stamp(e, tile_iter, 9);
+          }
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc) {
+            const int ncol = n0 + (c0 + cc) * 32;
+            if (c0 + cc >= NCH || ncol >= e.N) continue;  // warp-uniform
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + 4 * i));
+              o[4 * i + 0] = __uint_as_float(racc[cc][4 * i + 0]) + b.x;
+              o[4 * i + 1] = __uint_as_float(racc[cc][4 * i + 1]) + b.y;
+              o[4 * i + 2] = __uint_as_float(racc[cc][4 * i + 2]) + b.z;
+              o[4 * i + 3] = __uint_as_float(racc[cc][4 * i + 3]) + b.w;
+            }
+            if (e.act != MMVID_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = apply_act_fast(o[i], e.act);
+            }
+            if (e.residual) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                o[4 * i + 0] += res[cc][i].x; o[4 * i + 1] += res[cc][i].y;
+                o[4 * i + 2] += res[cc][i].z; o[4 * i + 3] += res[cc][i].w;
+              }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(st_base), "r"(ncol), "r"(m0 + q * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (e.residual && c0 + GRP < NCH) load_res(c0 + GRP);
+        }
+        if (etr) g2_stamp(e, tile_iter, 10);
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
+    } else {
     const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
     const uint32_t st_wr = st_base + (uint32_t)(lane * EPI_LD * 4);
     const int col = (lane & 7) * 4, rsub = lane >> 3;
     const uint32_t st_rd_row = st_base + (uint32_t)(rsub * EPI_LD * 4);
     const bool vec_ok = (e.N % 4 == 0) && (e.ldc % 4 == 0) && (!e.residual || e.ldr % 4 == 0);
-    constexpr int NCH = BN / 64;
+    constexpr int NCH = BN / 64;  // 32-column chunks per warp (half of the tile); 3 for the 192-wide tile
     uint32_t tile_iter = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
       const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
@@ -206,6 +319,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
+      const bool etr = (warp == 2 && lane == 0);
+      if (etr) g2_stamp(e, tile_iter, 8);
       const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
       const long long m_first = (long long)m0 + q * 32 + rsub;
 #pragma unroll
@@ -269,13 +384,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         }
         __syncwarp();
       }
+      if (etr) g2_stamp(e, tile_iter, 10);
     }
+    }  // !tma_store
   }
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc2(tmem_base, 2 * BN);
+    tmem_dealloc2(tmem_base, g2_tmem_cols<BN>());
   }
 }
 
@@ -295,7 +412,20 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStre
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
-  gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, e);
+  CUtensorMap tmC = tmA;  // placeholder when unused
+  e.tma_store = 0;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const char* ts = getenv("MMVID_GEMM_TMA_STORE");
+  if (!(ts && ts[0] == '0') && !e.c_bf16 && e.N % 32 == 0 && e.ldc % 4 == 0 && al16(e.C) &&
+      (!e.residual || (e.ldr % 4 == 0 && al16(e.residual))) && (!e.bias || al16(e.bias))) {
+    uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
+    uint64_t str[1] = {(uint64_t)e.ldc * 4};
+    uint32_t box[2] = {32, 32};
+    int rc = make_tensor_map(&tmC, e.C, DT_F32_EXACT, 2, dims, str, box);
+    if (rc) return rc;
+    e.tma_store = 1;
+  }
+  gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, e);
   return check_launch("gemm_tc2");
 }
 
@@ -327,6 +457,8 @@ extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const
   e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc; e.c_bf16 = c_dtype == MMVID_DT_BF16;
   e.M = M; e.N = N; e.K = K; e.act = act;
   { const char* v = getenv("MMVID_GEMM_SPIN"); e.spin = v ? atoi(v) : 0; }
+  e.trace = mmvid::g_gemm_trace;
   if (BN == 256) return tf32 ? launch2<true, 256>(tmA, tmB, e, st) : launch2<false, 256>(tmA, tmB, e, st);
+  if (BN == 192) return tf32 ? launch2<true, 192>(tmA, tmB, e, st) : launch2<false, 192>(tmA, tmB, e, st);
   return tf32 ? launch2<true, 128>(tmA, tmB, e, st) : launch2<false, 128>(tmA, tmB, e, st);
 }

@@ -35,7 +35,7 @@ if "--child" in sys.argv:   # one configuration in THIS process' environment: ge
     sys.exit(0)
 if "--2cta" in sys.argv:
     for prec in ("tf32", "bf16"):
-        for bn2 in (0, 128, 256):
+        for bn2 in (0, 128, 192, 256):
             env = dict(os.environ, MMVID_GEMM_2CTA=str(bn2))
             r = subprocess.run([sys.executable, "-c", CHILD, prec, json.dumps(SHAPES)], env=env, capture_output=True, text=True, timeout=300)
             print(prec, "2CTA BN", bn2, r.stdout.strip() or r.stderr[-800:], flush=True)
