@@ -428,7 +428,7 @@ def run_ours(args):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if dom == "attention" and args.precision == "tf32" and args.shape == "A" and B == 4:
-                traffic = tj["attention_tc2_kernel_tf32_shapeA_b4"]["dram_bytes_per_launch"]
+                traffic = tj["attention_tc3_kernel_tf32_shapeA_b4"]["dram_bytes_per_launch"]
         except Exception:
             traffic = None
         roof = {"bound": "tensor", "kernel": dom, "achieved": kr[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
