@@ -331,6 +331,10 @@ extern "C" int mmvid_attention_v5(const CUtensorMap* tq, const CUtensorMap* tk, 
                                   int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
                                   const int* host_prev_rows, int n_prev, int tf32, int poly8, int spin, int dual,
                                   int pingpong, unsigned long long* trace, cudaStream_t st);
+extern "C" int mmvid_attention_v6(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
+                                  int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
+                                  const int* host_prev_rows, int n_prev, int tf32, int poly8, unsigned long long* trace,
+                                  cudaStream_t st);
 namespace mmvid { extern unsigned long long* g_att_trace; }
 
 namespace {
@@ -369,11 +373,18 @@ extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, voi
     if (rc) return rc;
   }
   {
-    // MMVID_ATT_IMPL: 3 (default) = rotating-score-buffer kernel (tc_attention3.cu), 2 = two-tile ping-pong kernel
+    // MMVID_ATT_IMPL: 4 = persistent rotating-score-buffer kernel (tc_attention4.cu), 3 (default) = rotating-score-buffer
+    // kernel (tc_attention3.cu), 2 = two-tile ping-pong kernel
     // (tc_attention2.cu), 1 = the one-tile kernel below.  Measured defaults (profiles/r1_f_attention_v5.md): tf32 keeps
     // every exponential on MUFU, bf16 moves 2 of 8 to the FMA pipe.  MMVID_ATT_POLY (0|2|4 of every 8 exponentials on the
     // FMA pipe), MMVID_ATT_PP (0|1 MUFU ping-pong token) MMVID_ATT_SPIN (0|1) and MMVID_ATT_DUAL (0|1: one or two MMA-issuing threads) tune kernel 3.
-    const int impl = env_int("MMVID_ATT_IMPL", ATT_IMPL_DEFAULT);
+    int impl = env_int("MMVID_ATT_IMPL", ATT_IMPL_DEFAULT);
+    const int poly = env_int("MMVID_ATT_POLY", tf32 ? 0 : 2);
+    if (impl == 4 && S > 128 && (ldo * (out_dtype == MMVID_DT_BF16 ? 2 : 4)) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (poly == 0 || poly == 2))
+      return mmvid_attention_v6(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind, host_prev_rows,
+                                n_prev, tf32 ? 1 : 0, poly, mmvid::g_att_trace, to_stream(stream));
+    if (impl == 4) impl = 3;  // one key tile per item, odd output alignment or poly 4: the non-persistent kernel
     if (impl == 3)
       return mmvid_attention_v5(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind,
                                 host_prev_rows, n_prev, tf32 ? 1 : 0, env_int("MMVID_ATT_POLY", tf32 ? 0 : 2),

@@ -328,13 +328,29 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
       tmem_ld_wait();
       if (tr) att3_stamp(a, tb + 1);
       if (!tile_full) {
+        // the common partial tile is the LAST key tile of a bidirectional (BERT) sequence: no lower bound inside the tile and the
+        // same upper bound for every row.  Then whole 32-column chunks are either kept, dropped or (one of them) compared
+        // element by element - warp-uniform branches instead of 128 two-sided compares per thread.
+        const int nvalid = hi - kv0;
+        const int nvalid0 = __shfl_sync(0xffffffffu, nvalid, 0);  // (outside the && below: every lane must take part)
+        const bool simple = __all_sync(0xffffffffu, lo <= kv0 && nvalid == nvalid0);
+        if (simple) {
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
+          for (int ch = 0; ch < 4; ++ch) {
+            if ((ch + 1) * 32 <= nvalid) continue;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = kv0 + ch * 32 + i;
-            if (!(col >= lo && col < hi)) r[ch][i] = 0xff800000u;  // -inf
+            for (int i = 0; i < 32; ++i)
+              if (ch * 32 + i >= nvalid) r[ch][i] = 0xff800000u;  // -inf
           }
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = kv0 + ch * 32 + i;
+              if (!(col >= lo && col < hi)) r[ch][i] = 0xff800000u;  // -inf
+            }
+        }
       }
       float mx0 = __uint_as_float(r[0][0]), mx1 = __uint_as_float(r[0][1]);
 #pragma unroll

@@ -94,14 +94,14 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
     ms = sum(ts[:10]) / 10
     res["us"] = round(ms * 1000, 1)
     res["tflops"] = round(4.0 * S * S * H * 64 * B / ms / 1e9, 1)
-    if impl == "3" or impl == "2":
+    if impl in ("2", "3", "4"):
         buf = torch.zeros(512, dtype=torch.int64, device="cuda")
         L.check(lib.mmvid_debug_attention_trace(buf.data_ptr()))
         att()
         torch.cuda.synchronize()
         L.check(lib.mmvid_debug_attention_trace(None))
         t = buf.cpu().tolist()
-        if impl == "3":   # MMA rows: [2n] P(n) seen; steady-state period per key step = 2 tile-steps
+        if impl in ("3", "4"):   # MMA rows: [2n] P(n) seen; steady-state period per key step = 2 tile-steps
             res["period_clk"] = round((t[2 * 28] - t[2 * 8]) / 10.0)
         else:
             res["period_clk"] = round((t[14 * 4] - t[4 * 4]) / 10.0)
@@ -112,7 +112,7 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         return one(*sys.argv[2:8])
-    variants = [("2", "0", "0", "0", "0"), ("3", "0", "0", "1", "0"), ("3", "0", "0", "1", "1"), ("3", "2", "0", "1", "1"), ("3", "4", "0", "1", "1"), ("3", "2", "0", "0", "1")]
+    variants = [("2", "0", "0", "0", "0"), ("3", "0", "0", "1", "0"), ("3", "2", "0", "1", "0"), ("4", "0", "0", "1", "0"), ("4", "2", "0", "1", "0")]
     for prec in ("tf32", "bf16"):
         for impl, poly, spin, dual, pp in variants:
             try:

@@ -34,4 +34,10 @@ print(f"{prec} impl 3 poly {os.environ.get('MMVID_ATT_POLY', '0')}: n = 2j+g; MM
 for n in range(0, 34):
     j, g = n >> 1, n & 1
     sm = [t[128 + g * 192 + j * 6 + i] - t0 for i in range(6)]
-    print(f"n={n:2d} (j={j:2d} {'AB'[g]}) MMA seen {t[2 * n] - t0:6d} issued {t[2 * n + 1] - t0:6d} | softmax {sm}  busy {sm[5] - sm[0]}")
+    if n >= 30 or n < 6: print(f"n={n:2d} (j={j:2d} {'AB'[g]}) MMA seen {t[2 * n] - t0:6d} issued {t[2 * n + 1] - t0:6d} | softmax {sm}  busy {sm[5] - sm[0]}")
+
+if os.environ.get("MMVID_ATT_IMPL") == "4":
+    for g in range(2):
+        for I in range(4):
+            v = [t[480 + g * 16 + I * 4 + i] - t0 if t[480 + g * 16 + I * 4 + i] else -1 for i in range(4)]
+            print(f"item {I} tile {'AB'[g]}: start {v[0]} last P sent {v[1]} O complete {v[2]} stored {v[3]}")
