@@ -40,6 +40,8 @@ const char* mmvid_last_error(void);
 /* number of kernels this library has launched since load / last reset (bench.py "gpu_launches") */
 long long mmvid_launch_count(void);
 void mmvid_reset_launch_count(void);
+/* accounts for n kernels of this library that were replayed from a captured CUDA graph (they bypass the entry points) */
+void mmvid_add_launch_count(long long n);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  fused token + positional embedding gather  (reference: dalle_bert.py:903-972,1032-1036;

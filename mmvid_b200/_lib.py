@@ -43,6 +43,7 @@ SIGNATURES = {
     "mmvid_last_error": (C.c_char_p, []),
     "mmvid_launch_count": (_ll, []),
     "mmvid_reset_launch_count": (None, []),
+    "mmvid_add_launch_count": (None, [_ll]),
     "mmvid_embed_gather": (_i, [_p, _i, _i, _i, C.POINTER(EmbedSegment), _i, _p]),
     "mmvid_axial_table": (_i, [_p, _i, _i, _p, _p, _p, C.POINTER(_i), _i, _p]),
     "mmvid_layernorm": (_i, [_p, _ll, _p, _p, _p, _i, _ll, _i, _f, _p]),
@@ -120,3 +121,8 @@ def launch_count():
 
 def reset_launch_count():
     load().mmvid_reset_launch_count()
+
+
+def add_launch_count(n):
+    """Kernels of this library replayed from a captured CUDA graph (they do not pass through the entry points)."""
+    load().mmvid_add_launch_count(int(n))

@@ -14,6 +14,7 @@ extern "C" int mmvid_version(void) { return 100; }
 extern "C" const char* mmvid_last_error(void) { return g_err; }
 extern "C" long long mmvid_launch_count(void) { return g_launches.load(); }
 extern "C" void mmvid_reset_launch_count(void) { g_launches.store(0); }
+extern "C" void mmvid_add_launch_count(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------
 // K1 embedding gather: one warp-group row per block row; segments in constant-size param array.

@@ -595,6 +595,52 @@ class BERT(nn.Module):
         return torch.cat(sample_toks, 0), image_samples
 
     @torch.no_grad()
+    # ------------------------------------------------------------------------------------------ CUDA graph of one forward
+    def _use_cuda_graph(self, dev):
+        import os
+        return dev.type == "cuda" and os.environ.get("MMVID_CUDA_GRAPH", "1") != "0" and not torch.is_grad_enabled() \
+            and not torch.cuda.is_current_stream_capturing()
+
+    def _weights_version(self):
+        """Changes whenever a parameter is updated in place or replaced (training step, load_state_dict, .half())."""
+        v = 0
+        for p in self.parameters():
+            v = (v * 1000003 + p._version * 31 + p.data_ptr()) & 0xFFFFFFFFFFFF
+        return v
+
+    def _forward_graph(self, nb, dev):
+        """dict(graph, x [nb,S,D], ids [nb,Ttot], logits [nb,Ttot,1024]): target-embedding gather -> transformer ->
+        logits head captured in one CUDA graph.  Static buffers: the caller fills x[:, :control] and ids, replays,
+        and reads logits before the next replay (same stream)."""
+        key = (nb, str(dev), str(self.precision), str(self.transformer.precision), self._weights_version())
+        ent = getattr(self, "_graph_cache", None)
+        if ent is not None and ent["key"] == key:
+            return ent
+        D, Ttot, csl = self.dim, self.target_seq_len, self.control_seq_len
+        x = torch.zeros(nb, self.total_seq_len, D, device=dev, dtype=torch.float32)
+        ids = torch.full((nb, Ttot), self.image_token_lut["[MASK]"], dtype=torch.long, device=dev)
+
+        def fwd():
+            ops.embed_gather(x, [self._target_segment(ids)])
+            out = self.transformer(x)
+            return self._head(out[:, csl:].reshape(nb * Ttot, D), self.to_logits).view(nb, Ttot, -1)
+
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up: one-time kernel attributes, bf16 weight copies, Q/K/V buffers
+            fwd()
+            fwd()
+        cur.wait_stream(side)
+        from . import _lib
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            logits = fwd()
+        ent = dict(key=key, graph=graph, x=x, ids=ids, logits=logits, launches=_lib.launch_count() - n0)
+        self._graph_cache = ent
+        return ent
+
     def _mask_predict_batched(self, control_emb, steps, preserve, t_overlap, mp_config, long_mode):
         """Throughput variant of mask_predict: every sample advances in the same [B,S,D] forward.  Same algorithm
         per sample (beam 1, static schedule); RNG draws are made for the whole batch at once, so ids differ from
@@ -606,15 +652,30 @@ class BERT(nn.Module):
         N, pmask, ptok = self._preserve_setup(nb, preserve, t_overlap, long_mode, dev)
         Tmax = mp_config["T"] if steps <= 0 else steps
         n, temp = mask_predict_schedules(N, mp_config)
-        x = torch.empty(nb, self.total_seq_len, D, device=dev, dtype=torch.float32)
-        x[:, :csl].copy_(control_emb)
         valid_idx = torch.arange(Ttot, device=dev)[~pmask[0]]
+        # All Tmax forwards have the same shapes and read the same weights: the chain embed -> 12 layers -> head (~90
+        # launches) is captured ONCE per (batch, weights version) into a CUDA graph and replayed; only the token ids
+        # change, through a static buffer.  Removes the launch gaps between ~1800 short dependent kernels per call.
+        fg = self._forward_graph(nb, dev) if self._use_cuda_graph(dev) else None
+        if fg is not None:
+            from . import _lib as _lib_mod
+            x = fg["x"]
+            x[:, :csl].copy_(control_emb)
 
-        def run(ids_in, t):
-            ops.embed_gather(x, [self._target_segment(ids_in)])
-            out = self.transformer(x)
-            logits = self._head(out[:, csl:].reshape(nb * Ttot, D), self.to_logits).view(nb, Ttot, -1)
-            return self._sample_multinomial(logits, temp[t])
+            def run(ids_in, t):
+                fg["ids"].copy_(ids_in)
+                fg["graph"].replay()
+                _lib_mod.add_launch_count(fg["launches"])
+                return self._sample_multinomial(fg["logits"], temp[t])
+        else:
+            x = torch.empty(nb, self.total_seq_len, D, device=dev, dtype=torch.float32)
+            x[:, :csl].copy_(control_emb)
+
+            def run(ids_in, t):
+                ops.embed_gather(x, [self._target_segment(ids_in)])
+                out = self.transformer(x)
+                logits = self._head(out[:, csl:].reshape(nb * Ttot, D), self.to_logits).view(nb, Ttot, -1)
+                return self._sample_multinomial(logits, temp[t])
 
         tok_in = torch.where(pmask, ptok, torch.full_like(ptok, MASK))
         Y, I_new = run(tok_in, 0)
