@@ -179,7 +179,8 @@ typedef struct {
 int mmvid_conv2d(const mmvid_conv_params* p, mmvid_stream_t stream);
 
 /* K11 GroupNorm(32 groups, eps) + optional swish on NHWC (model.py:38-42, 33-35):
- *   stats scratch: mmvid_groupnorm_scratch_floats(N, groups) floats.  out may alias in. */
+ *   stats scratch: mmvid_groupnorm_scratch_floats(N, groups) floats.  out may alias in.
+ *   swish: 0 = none, 1 = x*sigmoid(x) with expf and IEEE division (fp32 parity mode), 2 = MUFU ex2 / rcp (~1e-6 relative). */
 int mmvid_groupnorm(const float* in, float* out, const float* gamma, const float* beta, float* stats_scratch,
                     int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream);
 
@@ -190,7 +191,8 @@ int mmvid_groupnorm_stats(const float* in, float* stats_scratch, int N, int HW, 
                           mmvid_stream_t stream);
 
 /* Decoder tail fused (model.py:578-581 + vae.py:55): GroupNorm + swish + 3x3 conv to Cout <= 4 channels
- * (+ clamp(-1,1)*0.5+0.5), NHWC in, NCHW out.  w packed [Cout,3,3,C]. */
+ * (+ clamp(-1,1)*0.5+0.5 when post_clamp bit 0 is set), NHWC in, NCHW out.  w packed [Cout,3,3,C].
+ * post_clamp bit 1: swish through MUFU ex2 / rcp instead of expf + IEEE division. */
 int mmvid_conv_out_fused(const float* in, const float* gamma, const float* beta, const float* w, const float* bias,
                          float* out, float* stats_scratch, int N, int H, int W, int C, int Cout, int groups, float eps,
                          int post_clamp, mmvid_stream_t stream);

@@ -421,6 +421,52 @@ __global__ void groupnorm_apply_kernel(const float4* __restrict__ in, float4* __
   }
 }
 
+// Streaming variant used when 256 % (C/4) == 0 (every VQGAN width): a thread keeps ONE channel quad for its whole life,
+// so gamma / beta / the (frame, group) statistics are loaded once per frame instead of once per element and there is
+// no 64-bit division in the loop; four pixels are in flight per thread.  ncu had the generic kernel above at 2.8 TB/s
+// (instruction bound: 64-bit div / mod, per-element statistic loads, accurate expf + IEEE division).
+// swish: 0 none, 1 x * sigmoid(x) with expf and IEEE division (fp32 parity mode), 2 MUFU ex2 + rcp (~1e-6 relative).
+template <int SWISH>
+__global__ void __launch_bounds__(256) groupnorm_apply2_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ stats, int HW, int C, int G) {
+  const int C4 = C >> 2, cpg = C / G;
+  const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, ppb = 256 / C4;
+  const int n = blockIdx.y, c = c4 * 4;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c)), bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+  const float g4[4] = {gm.x, gm.y, gm.z, gm.w}, b4[4] = {bt.x, bt.y, bt.z, bt.w};
+  float mean[4], rstd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int g = (c + j) / cpg;
+    mean[j] = stats[((long long)n * G + g) * 2];
+    rstd[j] = stats[((long long)n * G + g) * 2 + 1];
+  }
+  auto f = [&](float4 v) {
+    float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float y = (r[j] - mean[j]) * rstd[j] * g4[j] + b4[j];  // same operation order as the generic kernel
+      if (SWISH == 1) y = y / (1.f + expf(-y));
+      if (SWISH == 2) y = apply_act_fast(y, MMVID_ACT_SWISH);
+      r[j] = y;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+  };
+  const float4* src = in + (long long)n * HW * C4 + c4;
+  float4* dst = out + (long long)n * HW * C4 + c4;
+  const int step = gridDim.x * ppb;
+  int p = blockIdx.x * ppb + prow;
+  for (; p + 3 * step < HW; p += 4 * step) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = src[(long long)(p + u * step) * C4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dst[(long long)(p + u * step) * C4] = f(v[u]);
+  }
+  for (; p < HW; p += step) dst[(long long)p * C4] = f(src[(long long)p * C4]);
+}
+
 static int groupnorm_stats_launch(const float* in, float* stats, int N, int HW, int C, int groups, float eps,
                                   cudaStream_t st) {
   // scratch layout: [N*G*2 final stats][N*slabs*G*2 partials]
@@ -452,6 +498,18 @@ extern "C" int mmvid_groupnorm(const float* in, float* out, const float* gamma, 
   cudaStream_t st = to_stream(stream);
   int rc = groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, st);
   if (rc) return rc;
+  const int C4 = C / 4;
+  if (C4 <= 256 && 256 % C4 == 0 && N <= 65535) {
+    const int ppb = 256 / C4;
+    int gx = std::max(1, std::min(ceil_div(HW, ppb * 4), ceil_div(148 * 8, N)));
+    dim3 grid(gx, N);
+    const float4* i4 = (const float4*)in;
+    float4* o4 = (float4*)out;
+    if (swish == 0) groupnorm_apply2_kernel<0><<<grid, 256, 0, st>>>(i4, o4, gamma, beta, stats, HW, C, groups);
+    else if (swish == 2) groupnorm_apply2_kernel<2><<<grid, 256, 0, st>>>(i4, o4, gamma, beta, stats, HW, C, groups);
+    else groupnorm_apply2_kernel<1><<<grid, 256, 0, st>>>(i4, o4, gamma, beta, stats, HW, C, groups);
+    return check_launch("groupnorm_apply2");
+  }
   const long long total4 = (long long)N * HW * (C / 4);
   const int blocks = (int)std::min<long long>(ceil_div<long long>(total4, 256), 148 * 16);
   groupnorm_apply_kernel<<<blocks, 256, 0, st>>>((const float4*)in, (float4*)out, gamma, beta, stats, HW, C, groups,
@@ -468,6 +526,7 @@ extern "C" int mmvid_groupnorm(const float* in, float* out, const float* gamma, 
 // ------------------------------------------------------------------------------------------------
 constexpr int CO_TH = 16, CO_TW = 32, CO_CH = 32, CO_LD = 36;
 
+template <bool FAST>
 __global__ void __launch_bounds__(256) conv_out_fused_kernel(const float* __restrict__ in, const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ w /*[Cout][3][3][C]*/,
@@ -501,7 +560,7 @@ __global__ void __launch_bounds__(256) conv_out_fused_kernel(const float* __rest
           const int c = c0 + c4 * 4 + j, g = c / cpg;
           const float mean = stats[((long long)n * G + g) * 2], rstd = stats[((long long)n * G + g) * 2 + 1];
           float t = (r[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-          r[j] = t / (1.f + expf(-t));
+          r[j] = FAST ? apply_act_fast(t, MMVID_ACT_SWISH) : t / (1.f + expf(-t));
         }
         v = make_float4(r[0], r[1], r[2], r[3]);
       }
@@ -556,12 +615,18 @@ extern "C" int mmvid_conv_out_fused(const float* in, const float* gamma, const f
   const size_t smem = ((size_t)(CO_TH + 2) * (CO_TW + 2) * CO_LD + 4 * 9 * CO_CH) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(conv_out_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(conv_out_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(conv_out_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   dim3 grid(ceil_div(W, CO_TW), ceil_div(H, CO_TH), N);
-  conv_out_fused_kernel<<<grid, 256, smem, st>>>(in, stats_scratch, gamma, beta, w, bias, out, H, W, C, groups, Cout,
-                                                 post_clamp);
+  // post_clamp bit 0: clamp + rescale to [0, 1]; bit 1: swish through MUFU ex2 / rcp instead of expf + IEEE division
+  if (post_clamp & 2)
+    conv_out_fused_kernel<true><<<grid, 256, smem, st>>>(in, stats_scratch, gamma, beta, w, bias, out, H, W, C, groups, Cout,
+                                                         post_clamp & 1);
+  else
+    conv_out_fused_kernel<false><<<grid, 256, smem, st>>>(in, stats_scratch, gamma, beta, w, bias, out, H, W, C, groups, Cout,
+                                                          post_clamp & 1);
   return check_launch("conv_out_fused");
 }
 

@@ -105,8 +105,8 @@ def layernorm(x, weight, bias, eps=1e-5, out_dtype=torch.float32):
     return out.view(*x.shape[:-1], D)
 
 
-def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None):
-    """x: float32 [N, H, W, C] contiguous."""
+def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None, fast=False):
+    """x: float32 [N, H, W, C] contiguous.  fast: swish through MUFU ex2 / rcp (tensor-core precision modes)."""
     lib = L.load()
     _req(x_nhwc, torch.float32, "x")
     assert x_nhwc.is_contiguous()
@@ -114,7 +114,7 @@ def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None):
     out = torch.empty_like(x_nhwc) if out is None else out
     stats = torch.empty(int(lib.mmvid_groupnorm_scratch_floats(N, groups)), device=x_nhwc.device, dtype=torch.float32)
     L.check(lib.mmvid_groupnorm(_ptr(x_nhwc), _ptr(out), _ptr(weight), _ptr(bias), _ptr(stats), N, H * W, Cc, groups,
-                                eps, int(swish), _stream()), "groupnorm")
+                                eps, (2 if fast else 1) if swish else 0, _stream()), "groupnorm")
     return out
 
 
@@ -334,7 +334,7 @@ def upsample2x(x):
     return out
 
 
-def conv_out_fused(x_nhwc, gamma, beta, w_packed, bias, groups=32, eps=1e-6, post_clamp=True):
+def conv_out_fused(x_nhwc, gamma, beta, w_packed, bias, groups=32, eps=1e-6, post_clamp=True, fast=False):
     """GroupNorm + swish + 3x3 conv (Cout <= 4) + clamp/rescale; NHWC float32 in, NCHW out."""
     lib = L.load()
     _req(x_nhwc, torch.float32)
@@ -345,6 +345,6 @@ def conv_out_fused(x_nhwc, gamma, beta, w_packed, bias, groups=32, eps=1e-6, pos
     out = torch.empty(N, Cout, H, W, device=x_nhwc.device, dtype=torch.float32)
     stats = torch.empty(int(lib.mmvid_groupnorm_scratch_floats(N, groups)), device=x_nhwc.device, dtype=torch.float32)
     L.check(lib.mmvid_conv_out_fused(_ptr(x_nhwc), _ptr(gamma), _ptr(beta), _ptr(w_packed), _ptr(bias), _ptr(out),
-                                     _ptr(stats), N, H, W, Cc, Cout, groups, eps, int(post_clamp), _stream()),
+                                     _ptr(stats), N, H, W, Cc, Cout, groups, eps, int(post_clamp) | (2 if fast else 0), _stream()),
             "conv_out_fused")
     return out

@@ -214,9 +214,10 @@ class VQGanVAE1024(nn.Module):
         return FP32 if p == FP32 else TF32  # bf16 is not used inside the VQGAN: 1x1 convs run TF32 at most
 
     def _resblock(self, x, blk):
-        t = ops.groupnorm(x, blk.norm1.weight, blk.norm1.bias, swish=True)
+        fast = self._prec() != FP32  # tensor-core modes: MUFU sigmoid; fp32 parity mode keeps expf + IEEE division
+        t = ops.groupnorm(x, blk.norm1.weight, blk.norm1.bias, swish=True, fast=fast)
         t = self._conv3(t, blk.conv1)
-        t = ops.groupnorm(t, blk.norm2.weight, blk.norm2.bias, swish=True, out=t)
+        t = ops.groupnorm(t, blk.norm2.weight, blk.norm2.bias, swish=True, out=t, fast=fast)
         sc = x if blk.in_channels == blk.out_channels else self._conv1(x, blk.nin_shortcut)
         return self._conv3(t, blk.conv2, residual=sc)
 
@@ -288,7 +289,7 @@ class VQGanVAE1024(nn.Module):
                 h = self._conv3(h, up.upsample.conv, upsample=True)  # nearest x2 folded into the gather (model.py:56-62)
         # norm_out -> swish -> conv_out -> clamp/rescale in one pass over the 128-channel activation
         return ops.conv_out_fused(h, dec.norm_out.weight, dec.norm_out.bias, self._pack.conv(dec.conv_out.weight),
-                                  dec.conv_out.bias, post_clamp=True)
+                                  dec.conv_out.bias, post_clamp=True, fast=self._prec() != FP32)
 
     @torch.no_grad()
     def decode(self, img_seq):
