@@ -405,6 +405,7 @@ def run_ours(args):
         return float(t) / 1000.0  # seconds, max over ranks
 
     if args.profile:
+        os.environ["MMVID_CUDA_GRAPH"] = "0"  # launch list = exactly one step (a graph would add its warm-up forwards)
         step(False)
         torch.cuda.synchronize()
         if world > 1:

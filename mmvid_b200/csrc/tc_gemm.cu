@@ -599,6 +599,9 @@ extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const
                                 const float* bias, const float* residual, long long ldr, void* C, int c_dtype,
                                 long long ldc, long long M, int N, int K, int act, int precision, int BN, cudaStream_t st);
 
+extern "C" int mmvid_linear_qkv_tc2(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* q,
+                                    void* k, void* vt, int B, int H, int S, int S_pad, cudaStream_t st);
+
 namespace {
 struct QkvReq { void* q; void* k; void* vt; int S, Spad, H; };
 thread_local QkvReq g_qkv{nullptr, nullptr, nullptr, 0, 0, 0};
@@ -718,6 +721,12 @@ extern "C" int mmvid_linear_qkv(const void* A, int a_dtype, long long lda, const
                                 int S_pad, int precision, mmvid_stream_t stream) {
   MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16, "tensor-core precision required");
   MMVID_REQUIRE(S_pad >= S && S_pad % 64 == 0, "S_pad");
+  if (precision == MMVID_TF32 && out_dtype == MMVID_DT_F32 && a_dtype == MMVID_DT_F32 && w_dtype == MMVID_DT_F32 &&
+      env_int("MMVID_QKV_PAIR", 1)) {
+    // 256 x 256 CTA-pair tiles with the TMA-store scatter (tc_gemm2.cu); 1 = preconditions not met, use the kernel below
+    const int rc = mmvid_linear_qkv_tc2(A, lda, W, ldw, bias, q, k, vt, B, H, S, S_pad, to_stream(stream));
+    if (rc != 1) return rc;
+  }
   g_qkv = QkvReq{q, k, vt, S, S_pad, H};
   const int rc = mmvid_linear_tc(A, a_dtype, lda, W, w_dtype, ldw, bias, nullptr, 0, q /*unused*/, out_dtype, 0,
                                  (long long)B * S, 3 * H * 64, H * 64, MMVID_ACT_NONE, precision, to_stream(stream));

@@ -31,6 +31,10 @@ struct Epi2Args {
   int num_m_tiles /* 256-row tiles */, num_n_tiles;
   int spin;  // 1: TMA / MMA threads poll their ring barriers (see tc_gemm.cu)
   int tma_store;  // 1: fp32 result tiles leave through TMA bulk stores (same epilogue as tc_gemm.cu)
+  // QKV mode (qS > 0, TMA-store epilogue only): the [M, 3*H*64] result goes straight into the attention layout through
+  // tmQ / tmK (3-D {64, S_pad, B*H}) and tmV (2-D {S_pad, B*H*64}, transposed chunks); see the epilogue
+  int qS, qH, qB, qSpad;
+  float* qkv_q; float* qkv_k; float* qkv_vt;
   unsigned long long* trace;  // debug timeline of cluster 0's leader CTA (same layout as gemm_stamp in tc_gemm.cu)
 };
 
@@ -106,7 +110,8 @@ constexpr size_t g2_smem_bytes() {
 template <bool TF32, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, Epi2Args e) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmQ,
+                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, Epi2Args e) {
   constexpr int STAGES = g2_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -271,6 +276,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
+            if (e.qS > 0) {
+              // ---- fused QKV scatter.  A chunk is 32 tokens x 32 columns of one head (32 | 64): Q / K chunks are stored as
+              // they are into [B*H, S_pad, 64] by one 3-D TMA store.  The few chunks whose 32 tokens straddle a batch
+              // boundary (or the end of the last batch) are written row by row from registers instead: a TMA box cannot
+              // be clipped at S < S_pad, and the padding rows / columns must stay zero.
+              const int D = e.qH * 64;
+              const int which = ncol / D, hh = (ncol - which * D) >> 6, d0 = ncol & 63;
+              const int mb = m0 + q * 32;
+              const int bb = mb / e.qS, ss0 = mb - bb * e.qS;
+              // V^T chunks always go out from registers: for a fixed head-dim index the 32 lanes write 32 consecutive
+              // tokens (one coalesced 128-byte store), and a TMA box into V^T would need its first token 16-byte aligned,
+              // which an odd S rules out for every batch but the first (found the hard way: 'illegal instruction').
+              if (which == 2 || ss0 + 32 > e.qS || bb >= e.qB) {  // warp-uniform
+                const long long m = (long long)mb + lane;
+                if (m < e.M) {
+                  const int b2 = (int)(m / e.qS), s2 = (int)(m - (long long)b2 * e.qS);
+                  if (which < 2) {
+                    float* dst = (which == 0 ? e.qkv_q : e.qkv_k) + (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64 + d0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                      *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                  } else {
+                    float* dst = e.qkv_vt + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
+#pragma unroll
+                    for (int d = 0; d < 32; ++d) dst[(long long)d * e.qSpad] = o[d];
+                  }
+                }
+                continue;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                                 reinterpret_cast<uint64_t>(which == 0 ? &tmQ : &tmK)),
+                             "r"(st_base), "r"(d0), "r"(ss0), "r"(bb * e.qH + hh)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              continue;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -396,8 +444,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   }
 }
 
+struct QkvMaps { CUtensorMap q, k, v; };
+
 template <bool TF32, int BN>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStream_t st) {
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStream_t st, const QkvMaps* qm = nullptr) {
   static bool attr_set = false;
   constexpr size_t smem = g2_smem_bytes<BN>();
   if (!attr_set) {
@@ -416,7 +466,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStre
   e.tma_store = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const char* ts = getenv("MMVID_GEMM_TMA_STORE");
-  if (!(ts && ts[0] == '0') && !e.c_bf16 && e.N % 32 == 0 && e.ldc % 4 == 0 && al16(e.C) &&
+  if (qm == nullptr && !(ts && ts[0] == '0') && !e.c_bf16 && e.N % 32 == 0 && e.ldc % 4 == 0 && al16(e.C) &&
       (!e.residual || (e.ldr % 4 == 0 && al16(e.residual))) && (!e.bias || al16(e.bias))) {
     uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
     uint64_t str[1] = {(uint64_t)e.ldc * 4};
@@ -425,7 +475,12 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStre
     if (rc) return rc;
     e.tma_store = 1;
   }
-  gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, e);
+  if (qm != nullptr) {
+    e.tma_store = 1;  // the QKV scatter only exists in the TMA-store epilogue (the caller checked its preconditions)
+    gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmA, qm->q, qm->k, qm->v, e);
+    return check_launch("gemm_tc2_qkv");
+  }
+  gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, tmA, tmA, tmA, e);
   return check_launch("gemm_tc2");
 }
 
@@ -461,4 +516,55 @@ extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const
   if (BN == 256) return tf32 ? launch2<true, 256>(tmA, tmB, e, st) : launch2<false, 256>(tmA, tmB, e, st);
   if (BN == 192) return tf32 ? launch2<true, 192>(tmA, tmB, e, st) : launch2<false, 192>(tmA, tmB, e, st);
   return tf32 ? launch2<true, 128>(tmA, tmB, e, st) : launch2<false, 128>(tmA, tmB, e, st);
+}
+
+// Fused QKV projection on the CTA-pair kernel (tf32, fp32 Q / K / V^T): qkv = A W^T + b scattered straight into
+// Q, K [B,H,S_pad,64] and V^T [B,H,64,S_pad] by TMA stores.  Returns MMVID_EINVAL-free "not applicable" (1) when the
+// preconditions do not hold, so that mmvid_linear_qkv can fall back to the single-CTA kernel.
+extern "C" int mmvid_linear_qkv_tc2(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* q,
+                                    void* k, void* vt, int B, int H, int S, int S_pad, cudaStream_t st) {
+  const long long M = (long long)B * S;
+  const int N = 3 * H * 64, K = H * 64;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (S < 32 || N % 256 != 0 || M < 1024 || !al16(q) || !al16(k) || !al16(vt) || (bias && !al16(bias)) || S_pad % 4 != 0) return 1;
+  CUtensorMap tmA, tmB;
+  QkvMaps qm;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 4};
+    uint32_t box[2] = {32, (uint32_t)BM};
+    int rc = make_tensor_map(&tmA, A, MMVID_DT_F32, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldw * 4};
+    uint32_t box[2] = {32, 128};
+    int rc = make_tensor_map(&tmB, W, MMVID_DT_F32, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {64, (uint64_t)S_pad, (uint64_t)B * H};
+    uint64_t str[2] = {64 * 4, (uint64_t)S_pad * 64 * 4};
+    uint32_t box[3] = {32, 32, 1};
+    int rc = make_tensor_map(&qm.q, q, DT_F32_EXACT, 3, dims, str, box);
+    if (rc) return rc;
+    rc = make_tensor_map(&qm.k, k, DT_F32_EXACT, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)S_pad, (uint64_t)B * H * 64};
+    uint64_t str[1] = {(uint64_t)S_pad * 4};
+    uint32_t box[2] = {32, 32};
+    int rc = make_tensor_map(&qm.v, vt, DT_F32_EXACT, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  Epi2Args e{};
+  e.bias = bias; e.residual = nullptr; e.ldr = 0; e.C = nullptr; e.ldc = 0; e.c_bf16 = 0;
+  e.M = M; e.N = N; e.K = K; e.act = MMVID_ACT_NONE;
+  e.qS = S; e.qH = H; e.qB = B; e.qSpad = S_pad;
+  e.qkv_q = static_cast<float*>(q); e.qkv_k = static_cast<float*>(k); e.qkv_vt = static_cast<float*>(vt);
+  { const char* v = getenv("MMVID_GEMM_SPIN"); e.spin = v ? atoi(v) : 0; }
+  e.trace = mmvid::g_gemm_trace;
+  return launch2<true, 256>(tmA, tmB, e, st, &qm);
 }

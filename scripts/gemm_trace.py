@@ -1,6 +1,6 @@
 """Timeline of CTA 0 of the single-CTA tcgen05 GEMM at the benchmark shapes (clock64 stamps, see gemm_stamp in tc_gemm.cu)."""
 import os, sys
-os.environ.setdefault("MMVID_GEMM_2CTA", "1")   # keep every shape on the single-CTA kernel
+os.environ.setdefault("MMVID_GEMM_2CTA", "1")   # keep every shape on the single-CTA kernel (override: 128 | 192 | 256)
 import torch
 sys.path.insert(0, ".")
 from mmvid_b200 import _lib as L, ops
