@@ -339,3 +339,92 @@ def test_decode_kernels_match_full_attention():
     bias = torch.randn(100, generator=g).cuda()
     res = torch.randn(B, 100, generator=g).cuda()
     assert relerr(ops.linear_small_m(a, w, bias, residual=res), F.linear(a, w, bias) + res) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ round-1 additions
+@pytest.mark.parametrize("bn2", ["128", "192", "256"])
+@pytest.mark.parametrize("M,N,K,act,res", [(1400, 768, 3072, 0, True), (1300, 3072, 768, 1, False), (1100, 1024, 768, 0, False)])
+def test_cta_pair_tiles_with_tma_store_epilogue_match_fp64(monkeypatch, bn2, M, N, K, act, res):
+    """tc_gemm2.cu (cta_group::2 tiles 256 x 128 / 192 / 256, results through TMA bulk stores): bias, QuickGELU, residual and
+    the clipped M / N tails against an fp64 statement; the same call on the single-CTA kernel must agree as well."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + int(bn2))
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).cuda() if res else None
+    ref = F.linear(a.double(), w.double(), b.double())
+    if act:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    if res:
+        ref = ref + r.double()
+    monkeypatch.setenv("MMVID_GEMM_2CTA", bn2)
+    out = ops.linear(a, w, b, act=act, residual=r, precision="tf32")
+    monkeypatch.setenv("MMVID_GEMM_2CTA", "1")
+    one = ops.linear(a, w, b, act=act, residual=r, precision="tf32")
+    assert relerr(out, ref.float()) < TOL["tf32"]
+    assert relerr(out, one) < 1e-5
+    monkeypatch.setenv("MMVID_GEMM_TMA_STORE", "0")   # the transposing epilogue stays the fallback (bf16 outputs, odd N)
+    monkeypatch.setenv("MMVID_GEMM_2CTA", bn2)
+    old = ops.linear(a, w, b, act=act, residual=r, precision="tf32")
+    assert relerr(old, out) < 1e-5
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 700, 12), (3, 515, 12), (1, 1200, 12)])
+def test_fused_qkv_on_the_cta_pair_kernel_is_identical_to_the_single_cta_kernel(monkeypatch, B, S, H):
+    """M >= 1024 takes the 256 x 256 pair tile (Q / K by 3-D TMA stores, V^T from registers, batch-straddling chunks row
+    by row): same Q, K, V^T as the single-CTA scatter, zero padding untouched."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    D = H * 64
+    x = torch.randn(B * S, D, generator=g).cuda()
+    w = (torch.randn(3 * D, D, generator=g) / math.sqrt(D)).cuda()
+    b = torch.randn(3 * D, generator=g).cuda()
+    outs = []
+    for pair in ("1", "0"):
+        monkeypatch.setenv("MMVID_QKV_PAIR", pair)
+        bufs = ops.alloc_qkv_buffers(B, H, S, "tf32", "cuda")
+        ops.linear_qkv(x, w, b, bufs, B, S, H, "tf32")
+        outs.append([t.clone() for t in bufs])
+    ref = F.linear(x.double(), w.double(), b.double()).float().view(B, S, 3, H, 64)
+    (q, k, vt), (q0, k0, vt0) = outs
+    assert relerr(q[:, :, :S], ref[:, :, 0].permute(0, 2, 1, 3)) < TOL["tf32"]
+    assert relerr(vt[:, :, :, :S], ref[:, :, 2].permute(0, 2, 3, 1)) < TOL["tf32"]
+    for got, old in ((q, q0), (k, k0), (vt, vt0)):
+        assert relerr(got, old) < 1e-6
+    assert float(q[:, :, S:].abs().max()) == 0 and float(k[:, :, S:].abs().max()) == 0 and float(vt[:, :, :, S:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("impl,poly", [("2", "0"), ("3", "2"), ("4", "0"), ("4", "2")])
+def test_attention_kernel_generations_agree(monkeypatch, prec, impl, poly):
+    """v4 (P over S in place), v5 (rotating score buffers, the default) with FMA-pipe exponentials, v6 (persistent: 180
+    items for 148 CTAs, so some CTAs walk two items and the causal items have different lengths): all against the fp64
+    reference with both masks."""
+    ops = _ops()
+    from oracle import mmvid_oracle as O
+    B, S, H = 6, 1100, 6
+    g = torch.Generator().manual_seed(S)
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g).cuda()
+    monkeypatch.setenv("MMVID_ATT_IMPL", impl)
+    monkeypatch.setenv("MMVID_ATT_POLY", poly)
+    odt = torch.bfloat16 if prec == "bf16" else torch.float32
+    for kind, mk, rows in (("mask_prev", ops.MASK_PREV, (400, 401)), ("causal", ops.MASK_CAUSAL, ())):
+        mask = O.build_attention_mask(S, kind, rows) if kind == "mask_prev" else O.build_attention_mask(S, "causal")
+        ref = _attn_ref(qkv, B, S, H, mask)
+        out = ops.attention_tc(qkv, B, S, H, mk, rows, prec, out_dtype=odt).float()
+        assert relerr(out, ref) < TOL[prec], f"{prec} impl {impl} poly {poly} {kind}"
+
+
+def test_groupnorm_streaming_kernel_exact_and_fast_swish():
+    """groupnorm_apply2 (one channel quad per thread) for every VQGAN width, exact (expf / IEEE division) and MUFU swish."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    for C, HW in ((128, (24, 40)), (256, (16, 16)), (512, (8, 8))):
+        x = (torch.randn(3, HW[0], HW[1], C, generator=g) * 2 + 0.5).cuda()
+        w, b = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+        ref = F.group_norm(x.permute(0, 3, 1, 2).double(), 32, w.double(), b.double(), 1e-6)
+        ref_s = (ref * torch.sigmoid(ref)).permute(0, 2, 3, 1).float()
+        assert relerr(ops.groupnorm(x, w, b, swish=False), ref.permute(0, 2, 3, 1).float()) < 2e-5
+        assert relerr(ops.groupnorm(x, w, b, swish=True), ref_s) < 2e-5
+        assert relerr(ops.groupnorm(x, w, b, swish=True, fast=True), ref_s) < 2e-5

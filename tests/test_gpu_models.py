@@ -208,3 +208,28 @@ def test_artv_kv_cache_generate_matches_no_cache_oracle_on_gpu(reps, impl):
     assert torch.equal(toks, toks_o), "KV-cache decode must reproduce the reference's full re-forward sampling"
     fx = load_fixture("artv_tiny")
     assert images.shape[1:] == fx["gen_images"].shape[1:] and images.shape[0] == B
+
+
+def test_batched_mask_predict_cuda_graph_replay_equals_eager_launches(monkeypatch):
+    """The forward chain captured in a CUDA graph (static ids / x buffers) must produce exactly the ids and frames of the
+    launch-by-launch path under the same seed, also after the weights change (cache key = parameter versions)."""
+    cfg = BERT_CASES["bert_tiny_nov"]
+    model, _ = build_bert(cfg, precision="tf32", sampling_mode="batched")
+    text = synth.synth_text(4, cfg["text_seq_len"], cfg["vocab"], 3).cuda()
+    outs = {}
+    for sw in ("0", "1", "1"):
+        monkeypatch.setenv("MMVID_CUDA_GRAPH", sw)
+        torch.manual_seed(7)
+        im, _, s = model.generate_images(text, mask_predict_steps=5, dynamic=False)
+        if sw in outs:
+            assert torch.equal(outs[sw][1], s)  # second graphed call: replay of the cached graph
+        outs[sw] = (im, s)
+    assert torch.equal(outs["0"][1], outs["1"][1]) and torch.equal(outs["0"][0], outs["1"][0])
+    with torch.no_grad():
+        model.to_logits[1].bias.add_(0.5 * torch.randn_like(model.to_logits[1].bias))
+    res = {}
+    for sw in ("1", "0"):
+        monkeypatch.setenv("MMVID_CUDA_GRAPH", sw)
+        torch.manual_seed(7)
+        _, _, res[sw] = model.generate_images(text, mask_predict_steps=5, dynamic=False)
+    assert torch.equal(res["0"], res["1"]) and not torch.equal(res["1"], outs["1"][1])
