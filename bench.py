@@ -35,6 +35,29 @@ VOCAB = 49408
 DIM, LAYERS = 768, 12
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """From here on everything written to file descriptor 1 - Python prints AND C libraries such as NCCL, which prints its
+    version banner there - goes to stderr; the one JSON line is written to the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, line)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -139,7 +162,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": "video-tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def workload_config(args, per_gpu_batch):
@@ -455,7 +478,7 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1 and args.workload == "bert":
             out["cpu_baseline"] = cpu_reference_tokens_per_s(args.shape, args.mp_steps, n_fwd=2)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -463,6 +486,7 @@ def run_ours(args):
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
