@@ -120,7 +120,7 @@ constexpr size_t gemm_smem_bytes() {
 // Persistent, warp-specialised tcgen05 GEMM.  grid = min(#tiles, #SMs); every CTA walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so concurrently running CTAs share the same weight
 // tile in L2).  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue), tile loop.
-template <bool TF32, int BN, bool CONV>
+template <bool TF32, int BN, bool CONV, bool SWAP = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const __grid_constant__ CUtensorMap tmC, EpiArgs e) {
@@ -168,9 +168,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         int cx0 = 0, cy0 = 0, cn0 = 0;
         if constexpr (CONV) {
           // tiles never straddle rows partially: BW = min(W,128), BH = min(H,128/BW), BNI = 128/(BW*BH), W,H powers of 2
-          cx0 = m0 % e.cW;
-          cy0 = (m0 / e.cW) % e.cH;
-          cn0 = m0 / (e.cW * e.cH);
+          // (SWAP: the pixels are the N side of the tile, BN = 256 of them per box)
+          const int p0 = SWAP ? n0 : m0;
+          cx0 = p0 % e.cW;
+          cy0 = (p0 / e.cW) % e.cH;
+          cn0 = p0 / (e.cW * e.cH);
         }
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
@@ -178,6 +180,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           if (e.spin) mbar_wait_spin(&empty[s], ph ^ 1); else mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], STAGE_BYTES);
           uint8_t* a = tiles + s * STAGE_BYTES;
+          if constexpr (CONV && SWAP) {
+            // transposed tile: A slot = 128 output channels of the packed weights, B slot = 256 pixels through the 4-D box
+            const int tap = kb / cblocks, cb = kb - tap * cblocks;
+            const int ky = tap / e.cKW, kx = tap - ky * e.cKW;
+            tma_load_2d(a, &tmB, &full[s], kb * BKE, m0);
+            tma_load_4d(a + A_BYTES, &tmA, &full[s], cb * BKE, cx0 + kx - e.cPadL, cy0 + ky - e.cPadT, cn0);
+          } else {
           if constexpr (CONV) {
             const int tap = kb / cblocks, cb = kb - tap * cblocks;
             const int ky = tap / e.cKW, kx = tap - ky * e.cKW;
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             tma_load_2d(a, &tmA, &full[s], kb * BKE, m0);
           }
           tma_load_2d(a + A_BYTES, &tmB, &full[s], kb * BKE, n0);
+          }
           if (kb == 0) gemm_stamp(e, tma_tile, 16);
           if (kb == num_k - 1) gemm_stamp(e, tma_tile, 17);
         }
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
-        if (e.residual) load_res(0);
+        if (!SWAP && e.residual) load_res(0);
         mbar_wait(&tmem_full[acc], acc_ph);
         tc_fence_after();
         const bool etr = (warp == 2 && lane == 0);
@@ -283,8 +293,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int cc = 0; cc < GRP; ++cc) {
             const int ncol = n0 + (c0 + cc) * 32;
-            if (ncol >= e.N) continue;  // warp-uniform
+            if (!SWAP && ncol >= e.N) continue;  // warp-uniform
             float o[32];
+            if constexpr (SWAP) {
+              // transposed conv tile: this lane owns OUTPUT CHANNEL m0 + q*32 + lane, the chunk's 32 columns are pixels
+              // ncol .. ncol+31.  Bias is one scalar per lane, residual rows are read channel-contiguous (coalesced), and
+              // the chunk is transposed on its way into shared memory so that the bulk store writes NHWC rows.
+              const int cout = m0 + q * 32 + lane;
+              const float bv = e.bias ? __ldg(e.bias + cout) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                o[i] = __uint_as_float(racc[cc][i]) + bv;
+                if (e.residual) o[i] += e.residual[(long long)(ncol + i) * e.ldr + cout];
+              }
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)  // element (pixel row i, channel lane): 16-byte unit (lane >> 2) ^ (i & 7) of row i
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_base + (uint32_t)(i * 128 + ((((lane >> 2) ^ (i & 7)) << 4) | ((lane & 3) << 2)))),
+                             "f"(o[i])
+                             : "memory");
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                 reinterpret_cast<uint64_t>(&tmC)),
+                             "r"(st_base), "r"(m0 + q * 32), "r"(ncol)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              continue;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -321,7 +360,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
-          if (e.residual && c0 + GRP < NCH) load_res(c0 + GRP);
+          if (!SWAP && e.residual && c0 + GRP < NCH) load_res(c0 + GRP);
         }
         if (etr) gemm_stamp(e, tile_iter, 10);
       }
@@ -546,17 +585,21 @@ int pick_bn(long long M, int N, bool allow256 = true) {
   return best;
 }
 
-template <bool TF32, int BN, bool CONV = false>
+template <bool TF32, int BN, bool CONV = false, bool SWAP = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = gemm_smem_bytes<BN>();
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN, CONV, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(err));
     attr_set = true;
   }
   e.num_m_tiles = (int)ceil_div<long long>(e.M, BM);
   e.num_n_tiles = ceil_div(e.N, BN);
+  if (SWAP) {  // transposed conv tile: "m" tiles walk the output channels (128 each), "n" tiles the pixels (BN each)
+    e.num_m_tiles = e.N / BM;
+    e.num_n_tiles = (int)(e.M / BN);
+  }
   e.spin = env_int("MMVID_GEMM_SPIN", GEMM_SPIN_DEFAULT);
   e.trace = g_gemm_trace;
   e.raster = env_int("MMVID_GEMM_RASTER", 1);  // n fastest: consecutive CTAs share the activation tile (measured best)
@@ -575,7 +618,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream
   }
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  gemm_tc_kernel<TF32, BN, CONV><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, e);
+  if (SWAP && !e.tma_store) return fail(MMVID_EINVAL, "transposed conv tile needs the TMA-store epilogue%s");
+  gemm_tc_kernel<TF32, BN, CONV, SWAP><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, e);
   return check_launch("gemm_tc");
 }
 
@@ -683,11 +727,42 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
                 "tc conv: stride 1, NHWC, no fused resampling");
   MMVID_REQUIRE(p->Cin % 32 == 0 && p->Cout % 4 == 0, "tc conv: Cin % 32 == 0, Cout % 4 == 0");
   MMVID_REQUIRE(pow2(p->H) && pow2(p->W) && p->Ho == p->H && p->Wo == p->W, "tc conv: power-of-two 'same' convolution");
+  const long long M = (long long)p->N * p->H * p->W;
+  const int K = p->KH * p->KW * p->Cin;
+  // EXPERIMENTAL (MMVID_CONV_SWAP=1, not validated on hardware yet): transposed tile for the Cout = 128 layers - A = 128
+  // output channels of the packed weights, B = 256 pixels - so that the MMA is 256 wide and leaves the ~100 clk SS floor
+  // (profiles/r1_g_gemm_pipeline.md); the result chunk is transposed in shared memory before the bulk store.
+  if (env_int("MMVID_CONV_SWAP", 0) && p->Cout % 128 == 0 && M % 256 == 0) {
+    const int BW2 = p->W < 256 ? p->W : 256;
+    const int BH2 = (256 / BW2) < p->H ? (256 / BW2) : p->H;
+    const int BNI2 = 256 / (BW2 * BH2);
+    if (BNI2 >= 1 && p->N % BNI2 == 0) {
+      CUtensorMap tmX, tmW;
+      {
+        uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+        uint64_t str[3] = {(uint64_t)p->Cin * 4, (uint64_t)p->W * p->Cin * 4, (uint64_t)p->H * p->W * p->Cin * 4};
+        uint32_t box[4] = {32, (uint32_t)BW2, (uint32_t)BH2, (uint32_t)BNI2};
+        int rc = make_tensor_map(&tmX, p->in, MMVID_DT_F32, 4, dims, str, box);
+        if (rc) return rc;
+      }
+      {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)p->Cout};
+        uint64_t str[1] = {(uint64_t)K * 4};
+        uint32_t box[2] = {32, 128};
+        int rc = make_tensor_map(&tmW, p->w, MMVID_DT_F32, 2, dims, str, box);
+        if (rc) return rc;
+      }
+      EpiArgs e{};
+      e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_bf16 = 0;
+      e.M = M; e.N = p->Cout; e.K = K; e.act = MMVID_ACT_NONE;
+      e.cCin = p->Cin; e.cKW = p->KW; e.cPadT = p->pad_t; e.cPadL = p->pad_l; e.cBW = BW2; e.cBH = BH2; e.cBNI = BNI2;
+      e.cW = p->W; e.cH = p->H;
+      return launch<true, 256, true, true>(tmX, tmW, e, st);
+    }
+  }
   const int BW = p->W < 128 ? p->W : 128;
   const int BH = (128 / BW) < p->H ? (128 / BW) : p->H;
   const int BNI = 128 / (BW * BH);
-  const long long M = (long long)p->N * p->H * p->W;
-  const int K = p->KH * p->KW * p->Cin;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
