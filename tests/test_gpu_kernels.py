@@ -428,3 +428,22 @@ def test_groupnorm_streaming_kernel_exact_and_fast_swish():
         assert relerr(ops.groupnorm(x, w, b, swish=False), ref.permute(0, 2, 3, 1).float()) < 2e-5
         assert relerr(ops.groupnorm(x, w, b, swish=True), ref_s) < 2e-5
         assert relerr(ops.groupnorm(x, w, b, swish=True, fast=True), ref_s) < 2e-5
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MMVID_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: code paths written after round 1's GPU budget ran out (MMVID_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 128, 128, 32), (1, 256, 128, 128), (4, 128, 256, 16), (8, 512, 512, 8)])
+def test_experimental_transposed_conv_tile_matches_fp64(monkeypatch, N, Cin, Cout, H):
+    """MMVID_CONV_SWAP=1: 128 output channels x 256 pixels per tile (256-wide MMA), result chunks transposed before the
+    bulk store.  Same reference and tolerance as the production conv test."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 1000 + Cin + H)
+    x = torch.randn(N, Cin, H, H, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, H, H, Cout, generator=g).cuda()
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    monkeypatch.setenv("MMVID_CONV_SWAP", "1")
+    assert relerr(ops.conv2d(xn, _pack(w), b, precision="tf32"), ref) < 1e-3
+    assert relerr(ops.conv2d(xn, _pack(w), b, residual=res, precision="tf32"), ref + res) < 1e-3
