@@ -115,3 +115,28 @@ def test_shard_bounds_cover_batch_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py's contract: rank 0 prints ONE JSON line.  Python prints, C-level writes to fd 1 (NCCL's version banner) and
+    child processes must end up on stderr once quiet_stdout() ran; emit() writes the line to the saved descriptor."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, os, subprocess\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import bench\n"
+        "bench.quiet_stdout()\n"
+        "print('python noise')\n"
+        "os.write(1, b'C-level noise\\n')\n"
+        "subprocess.run(['echo', 'child noise'])\n"
+        "bench.emit({'metric': 'm', 'value': 1.5})\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert json.loads(r.stdout) == {"metric": "m", "value": 1.5} and r.stdout.count("\n") == 1
+    for noise in ("python noise", "C-level noise", "child noise"):
+        assert noise in r.stderr
