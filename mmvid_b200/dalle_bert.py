@@ -637,7 +637,11 @@ class BERT(nn.Module):
         n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
             logits = fwd()
-        ent = dict(key=key, graph=graph, x=x, ids=ids, logits=logits, launches=_lib.launch_count() - n0)
+        # The graph holds raw pointers: keep every tensor it reads or writes alive for as long as the graph lives, even if
+        # a later forward of another shape makes the transformer replace its cached Q / K / V^T buffers or bf16 copies.
+        keep = [getattr(self.transformer, "_qkv_bufs", None), self.target_pos_emb.table(),
+                list(self.transformer._bf16._d.values())]
+        ent = dict(key=key, graph=graph, x=x, ids=ids, logits=logits, launches=_lib.launch_count() - n0, keep=keep)
         self._graph_cache = ent
         return ent
 
