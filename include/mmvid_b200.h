@@ -242,6 +242,11 @@ int mmvid_debug_attention_trace(unsigned long long* dev_buf);
  * clock64() stamps of its first 8 tiles into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/gemm_trace.py. */
 int mmvid_debug_gemm_trace(unsigned long long* dev_buf);
 
+/* Host-only hook (no launch): the tile mmvid_linear picks for a plain tensor-core GEMM of this shape: 2000 + BN = CTA-pair
+ * kernel with a 256 x BN tile, 1000 + BN = single-CTA kernel with a 128 x BN tile.  precision: MMVID_TF32 | MMVID_BF16,
+ * c_dtype: MMVID_DT_F32 | MMVID_DT_BF16. */
+int mmvid_debug_pick_tile(long long M, int N, int K, int precision, int c_dtype);
+
 /* Profiling hook: clock64() cost of n_mma back-to-back tcgen05.mma of one shape on one SM (flavors: see
  * csrc/debug_mma_rate.cu); dev_out[0] = issue cycles, dev_out[1] = cycles until the commit barrier fires. */
 int mmvid_debug_mma_rate(int flavor, int n_mma, unsigned long long* dev_out, mmvid_stream_t stream);

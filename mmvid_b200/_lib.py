@@ -83,6 +83,7 @@ SIGNATURES = {
     "mmvid_debug_attention_trace": (_i, [_p]),
     "mmvid_debug_mma_rate": (_i, [_i, _i, _p, _p]),
     "mmvid_debug_gemm_trace": (_i, [_p]),
+    "mmvid_debug_pick_tile": (_i, [_ll, _i, _i, _i, _i]),
     "mmvid_grad_sqnorm": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "mmvid_grad_clip": (_i, [_p, _p, _p, _i, _i, _p, _f, _p]),
     "mmvid_adam_step": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _f, _i, _i, _p]),

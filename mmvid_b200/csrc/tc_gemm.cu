@@ -632,6 +632,41 @@ int launch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiA
 
 }  // namespace
 
+namespace {
+// CTA-pair (cta_group::2, tc_gemm2.cu) tile for this problem: 0 = none (single-CTA kernel), else 128 | 192 | 256 columns.
+// MMVID_GEMM_2CTA=128|192|256 forces it everywhere, =1 disables it.
+int pick_pair_bn(long long M, int N, int K, bool tf32, int c_dtype) {
+  int bn2 = env_int("MMVID_GEMM_2CTA", 0);
+  if (bn2 == 0 && c_dtype == MMVID_DT_F32 && N >= 512 && M >= 1024) {
+    // An SS tcgen05.mma costs ~100 clk whatever its N (r1q-r1v traces: 380-430 clk per 4-instruction k-block for N = 128,
+    // 192 and 256 alike; the 128-row A slice fetch from shared memory is the floor), so only instructions with >= 100 clk
+    // of work run the tensor pipe at its rate: 256 x 192 / 256 x 256 CTA-pair tiles.  With the TMA-store epilogue these
+    // tiles are no longer epilogue bound (c_fc 80 -> 72 us, c_proj 72 -> 67 us).  Per-tile costs in k clk from the traces.
+    const int sms = num_sms();
+    const long long mt = ceil_div<long long>(M, BM), mt2 = ceil_div<long long>(M, 2 * BM);
+    const double c128 = (double)ceil_div<long long>(mt * ceil_div(N, 128), sms) * 11.2;
+    const double c256 = tf32 ? (double)ceil_div<long long>(mt * ceil_div(N, 256), sms) * 17.1 : 1e30;
+    const double p192 = (double)ceil_div<long long>(mt2 * ceil_div(N, 192), sms / 2) * 11.8;
+    const double p256 = (double)ceil_div<long long>(mt2 * ceil_div(N, 256), sms / 2) * 13.2;
+    const double best1 = c128 < c256 ? c128 : c256;
+    if (p256 <= p192 && p256 < best1) bn2 = 256;
+    else if (p192 < p256 && p192 < best1) bn2 = 192;
+  }
+  // long-K GEMMs: the 256 x 128 pair tile measured 7-9 % faster than the single-CTA tile (deeper TMA ring)
+  if (bn2 == 0 && K >= 2048 && M >= 1024 && N >= 256) bn2 = 128;
+  return (bn2 == 128 || bn2 == 192 || bn2 == 256) ? bn2 : 0;
+}
+
+}  // namespace
+
+// Debug hook (host only, no launch): which tile mmvid_linear would pick for a plain (non-QKV) tensor-core GEMM:
+// 2000 + BN = CTA-pair kernel with a 256 x BN tile, 1000 + BN = single-CTA kernel with a 128 x BN tile.
+extern "C" int mmvid_debug_pick_tile(long long M, int N, int K, int precision, int c_dtype) {
+  const bool tf32 = precision == MMVID_TF32;
+  const int bn2 = pick_pair_bn(M, N, K, tf32, c_dtype);
+  return bn2 ? 2000 + bn2 : 1000 + pick_bn(M, N, tf32);
+}
+
 // Debug / profiling hook: CTA 0 of every following single-CTA tensor-core GEMM launch writes clock64() stamps of its
 // first 8 tiles into dev_buf (>= 512 entries; NULL switches it off).  Layout: gemm_stamp above.
 extern "C" int mmvid_debug_gemm_trace(unsigned long long* dev_buf) {
@@ -668,24 +703,8 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
     // CTA-pair (cta_group::2, tc_gemm2.cu) kernel for long-K GEMMs (c_proj: K = 3072 measured 7-9 % faster than the
     // single-CTA tile; short-K GEMMs are bounded by their output stream and gain nothing).  MMVID_GEMM_2CTA=128|256
     // forces it everywhere, =1 disables it.
-    int bn2 = env_int("MMVID_GEMM_2CTA", 0);
-    if (bn2 == 0 && c_dtype == MMVID_DT_F32 && N >= 512 && M >= 1024) {
-      // An SS tcgen05.mma costs ~100 clk whatever its N (r1q-r1v traces: 380-430 clk per 4-instruction k-block for N = 128,
-      // 192 and 256 alike; the 128-row A slice fetch from shared memory is the floor), so only instructions with >= 100 clk
-      // of work run the tensor pipe at its rate: 256 x 192 / 256 x 256 CTA-pair tiles.  With the TMA-store epilogue these
-      // tiles are no longer epilogue bound (c_fc 80 -> 72 us, c_proj 72 -> 67 us).  Per-tile costs in k clk from the traces.
-      const int sms = num_sms();
-      const long long mt = ceil_div<long long>(M, BM), mt2 = ceil_div<long long>(M, 2 * BM);
-      const double c128 = (double)ceil_div<long long>(mt * ceil_div(N, 128), sms) * 11.2;
-      const double c256 = tf32 ? (double)ceil_div<long long>(mt * ceil_div(N, 256), sms) * 17.1 : 1e30;
-      const double p192 = (double)ceil_div<long long>(mt2 * ceil_div(N, 192), sms / 2) * 11.8;
-      const double p256 = (double)ceil_div<long long>(mt2 * ceil_div(N, 256), sms / 2) * 13.2;
-      const double best1 = c128 < c256 ? c128 : c256;
-      if (p256 <= p192 && p256 < best1) bn2 = 256;
-      else if (p192 < p256 && p192 < best1) bn2 = 192;
-    }
-    if (bn2 == 0 && K >= 2048 && M >= 1024 && N >= 256) bn2 = 128;
-    if ((bn2 == 128 || bn2 == 192 || bn2 == 256) && g_qkv.q == nullptr)
+    const int bn2 = pick_pair_bn(M, N, K, tf32, c_dtype);
+    if (bn2 != 0 && g_qkv.q == nullptr)
       return mmvid_linear_tc2(A, a_dtype, lda, W, w_dtype, ldw, bias, residual, ldr, C, c_dtype, ldc, M, N, K, act, precision,
                               bn2, st);
   }

@@ -140,3 +140,24 @@ def test_bench_stdout_carries_only_the_json_line():
     assert json.loads(r.stdout) == {"metric": "m", "value": 1.5} and r.stdout.count("\n") == 1
     for noise in ("python noise", "C-level noise", "child noise"):
         assert noise in r.stderr
+
+
+def test_gemm_tile_picker_on_the_benchmark_shapes():
+    """Host-only dispatch of mmvid_linear (no GPU needed: 148 SMs are assumed without a device).  2000 + BN = CTA-pair kernel
+    with a 256 x BN tile, 1000 + BN = single-CTA kernel.  The benchmark's layers must land on the tiles the pipeline traces
+    selected (profiles/r1_g_gemm_pipeline.md); small problems stay on small single-CTA tiles; bf16 OUTPUTS stay single-CTA
+    (their epilogue is not a TMA store yet)."""
+    from mmvid_b200 import _lib as L
+    lib = L.load()
+    TF32, BF16, F32, B16 = L.TF32, L.BF16, L.DT_F32, L.DT_BF16
+    pick = lib.mmvid_debug_pick_tile
+    M = 4 * 2115
+    assert pick(M, 3072, 768, TF32, F32) == 2256       # c_fc
+    assert pick(M, 768, 3072, TF32, F32) == 2192       # c_proj: 136 tiles of 256 x 192 for 74 pairs instead of 102 of 256 x 256
+    assert pick(M, 768, 768, TF32, F32) == 2192        # out_proj
+    assert pick(4 * 2048, 1024, 768, TF32, F32) == 2256  # logits head
+    assert pick(M, 3072, 768, BF16, B16) == 1128       # bf16 output, short K: single CTA
+    assert pick(M, 768, 3072, BF16, B16) == 2128       # bf16 output, long K: 256 x 128 pair (deeper TMA ring)
+    assert pick(M, 768, 3072, BF16, F32) == 2192       # bf16 operands, fp32 residual stream
+    assert pick(130, 192, 128, TF32, F32) == 1064      # tiny problem: most CTAs
+    assert pick(0, 192, 128, TF32, F32) // 1000 == 1
