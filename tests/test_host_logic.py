@@ -161,3 +161,32 @@ def test_gemm_tile_picker_on_the_benchmark_shapes():
     assert pick(M, 768, 3072, BF16, F32) == 2192       # bf16 operands, fp32 residual stream
     assert pick(130, 192, 128, TF32, F32) == 1064      # tiny problem: most CTAs
     assert pick(0, 192, 128, TF32, F32) // 1000 == 1
+
+
+def test_fma_pipe_exp2_polynomial_accuracy_claims():
+    """Bit-level numpy restatement of exp2_poly2 (tc_attention3.cu): clamp at -126, round-to-nearest through the 1.5 * 2^23
+    magic constant, minimax polynomial on [-0.5, 0.5], exponent added as an integer.  Pins the accuracy the kernel's header
+    claims (degree 4: 2.7e-6 for the tf32 path, degree 3: 7.5e-5 for the bf16 path) and the behaviour at the edges."""
+    import numpy as np
+    f32 = np.float32
+    coef = {4: [0.9999992847442627, 0.6931217908859253, 0.240247443318367, 0.05591785907745361, 0.009570101276040077],
+            3: [0.9999280571937561, 0.6932609677314758, 0.2426111251115799, 0.0551716648042202]}
+
+    def exp2_poly(x, deg):
+        x = np.maximum(x.astype(f32), f32(-126.0))
+        t = (x + f32(12582912.0)).astype(f32)
+        f = (x - (t - f32(12582912.0)).astype(f32)).astype(f32)
+        p = np.full_like(f, f32(coef[deg][-1]))
+        for c in coef[deg][-2::-1]:
+            p = (p * f + f32(c)).astype(f32)
+        bits = p.view(np.uint32) + (t.view(np.uint32) << np.uint32(23))
+        return bits.view(f32)
+
+    x = np.linspace(-60.0, 8.9, 2_000_001).astype(f32)   # scores after max subtraction, up to the lazy-rescale slack
+    ref = np.exp2(x.astype(np.float64))
+    for deg, bound in ((4, 3.0e-6), (3, 8.0e-5)):
+        rel = np.abs(exp2_poly(x, deg).astype(np.float64) / ref - 1.0)
+        assert rel.max() < bound, (deg, rel.max())
+    # masked keys (-inf) and very negative scores give a tiny positive number instead of an exponent-field borrow
+    edge = exp2_poly(np.array([-np.inf, -1e30, -126.0, -125.7], dtype=f32), 4)
+    assert np.all(edge >= 0) and np.all(edge < 3e-38)
