@@ -55,6 +55,8 @@ typedef struct {
   const int64_t* ids; long long ids_bstride; int n; int seq_off;
   const float* table; const float* table2; const float* pos;
   long long pad_value; long long pad_base; int use_pad;
+  long long table_rows; /* rows of table (and table2): an id outside [0, table_rows) traps the kernel, which surfaces as a
+                           CUDA error at the next synchronisation (torch's nn.Embedding device assert); 0 = unchecked */
 } mmvid_embed_segment;
 int mmvid_embed_gather(float* out, int B, int S, int D, const mmvid_embed_segment* host_segments, int num_segments,
                        mmvid_stream_t stream);
@@ -155,9 +157,10 @@ int mmvid_artv_decode_fused(const mmvid_decode_layer* host_layers, int n_layers,
  * K14  VQ nearest-codeword lookup (taming/modules/vqvae/quantize.py:302-311):
  *   d[t,j] = (sum z_t^2 + sum e_j^2) - 2 z_t.e_j   in fp32, this association; idx[t] = argmin_j (lowest index wins)
  *   z: [T, dim] (NHWC rows); codebook [n_codes, dim]; idx int64 [T]
+ *   e2_scratch: caller-owned device floats [n_codes] (||e||^2; callers on different streams pass different buffers)
  * ---------------------------------------------------------------------------------------------- */
-int mmvid_vq_argmin(const float* z, const float* codebook, int64_t* idx, long long T, int n_codes, int dim,
-                    mmvid_stream_t stream);
+int mmvid_vq_argmin(const float* z, const float* codebook, int64_t* idx, float* e2_scratch, long long T, int n_codes,
+                    int dim, mmvid_stream_t stream);
 
 /* K15 codebook gather for decode (vae.py:50-52): out[t, :] = codebook[ids[t], :]  (NHWC rows) */
 int mmvid_codebook_gather(const int64_t* ids, const float* codebook, float* out, long long T, int dim,

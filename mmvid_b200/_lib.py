@@ -16,10 +16,23 @@ PRECISIONS = {"fp32": FP32, "tf32": TF32, "bf16": BF16}
 
 _p, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 
+# Kernels that update parameters through raw pointers (optim.FusedAdam) do not advance torch's per-tensor version
+# counters, so every cache of derived weights (axial tables, 16-bit copies, repacked conv weights, captured CUDA graphs)
+# keys on (data_ptr, _version, weights_epoch()); such kernels call bump_weights_epoch() after their launch.
+_weights_epoch = [0]
+
+
+def weights_epoch():
+    return _weights_epoch[0]
+
+
+def bump_weights_epoch():
+    _weights_epoch[0] += 1
+
 
 class EmbedSegment(C.Structure):
     _fields_ = [("ids", _p), ("ids_bstride", _ll), ("n", _i), ("seq_off", _i), ("table", _p), ("table2", _p),
-                ("pos", _p), ("pad_value", _ll), ("pad_base", _ll), ("use_pad", _i)]
+                ("pos", _p), ("pad_value", _ll), ("pad_base", _ll), ("use_pad", _i), ("table_rows", _ll)]
 
 
 class DecodeLayer(C.Structure):
@@ -61,7 +74,7 @@ SIGNATURES = {
     "mmvid_artv_decode_step": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mmvid_artv_decode_persistent": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mmvid_artv_decode_fused": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "mmvid_vq_argmin": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
+    "mmvid_vq_argmin": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),
     "mmvid_groupnorm": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),

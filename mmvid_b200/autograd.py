@@ -197,6 +197,7 @@ class EmbedFn(torch.autograd.Function):
         seg.ids, seg.ids_bstride, seg.n, seg.seq_off = ids.data_ptr(), (ids.stride(0) if ids.shape[0] == B else 0), ids.shape[1], seq_off
         if pad is not None:
             seg.pad_value, seg.pad_base, seg.use_pad = pad[0], pad[1], 1
+        seg.table_rows = ts[0]
         L.check(lib.mmvid_embed_backward(_p(dx), B, S_total, D, C.byref(seg), _p(dt), _p(dt2), _p(dp), _s()), "embed_backward")
         return dt, dt2, dp, None, None, None, None, None, None
 

@@ -34,6 +34,7 @@ __global__ void embed_gather_kernel(float* __restrict__ out, int S, int D, Embed
   const mmvid_embed_segment& g = p.seg[s];
   long long id = g.ids[(long long)b * g.ids_bstride + r];
   if (g.use_pad && id == g.pad_value) id = g.pad_base + r;
+  if (g.table_rows > 0 && (id < 0 || id >= g.table_rows)) __trap();  // nn.Embedding raises on such an id
   const float4* t = reinterpret_cast<const float4*>(g.table + id * (long long)D);
   const float4* t2 = g.table2 ? reinterpret_cast<const float4*>(g.table2 + id * (long long)D) : nullptr;
   const float4* ps = g.pos ? reinterpret_cast<const float4*>(g.pos + (long long)r * D) : nullptr;
@@ -719,16 +720,11 @@ __global__ void vq_argmin_kernel(const float* __restrict__ z, const float* __res
   }
 }
 
-// scratch for ||e||^2 lives in a small static device buffer (n_codes <= 16384)
-__device__ float g_e2_scratch[16384];
-
-extern "C" int mmvid_vq_argmin(const float* z, const float* codebook, int64_t* idx, long long T, int n_codes, int dim,
-                               mmvid_stream_t stream) {
+extern "C" int mmvid_vq_argmin(const float* z, const float* codebook, int64_t* idx, float* e2, long long T, int n_codes,
+                               int dim, mmvid_stream_t stream) {
   MMVID_REQUIRE(dim % 4 == 0 && dim <= 1024, "dim multiple of 4");
-  MMVID_REQUIRE(n_codes <= 16384, "n_codes <= 16384");
+  MMVID_REQUIRE(e2 != nullptr, "e2_scratch [n_codes] is caller-owned");
   if (T == 0) return MMVID_OK;
-  float* e2 = nullptr;
-  cudaGetSymbolAddress((void**)&e2, g_e2_scratch);
   cudaStream_t st = to_stream(stream);
   code_sqnorm_kernel<<<ceil_div(n_codes, 8), 256, 0, st>>>(codebook, e2, n_codes, dim);
   int rc = check_launch("code_sqnorm");
@@ -958,6 +954,7 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, int S, int D, mmv
   const int r = blockIdx.x, b = blockIdx.y;
   long long id = g.ids[(long long)b * g.ids_bstride + r];
   if (g.use_pad && id == g.pad_value) id = g.pad_base + r;
+  if (g.table_rows > 0 && (id < 0 || id >= g.table_rows)) __trap();
   const float* src = dx + ((long long)b * S + g.seq_off + r) * D;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     const float v = src[c];

@@ -594,7 +594,6 @@ class BERT(nn.Module):
             sample_toks.append(Imax)
         return torch.cat(sample_toks, 0), image_samples
 
-    @torch.no_grad()
     # ------------------------------------------------------------------------------------------ CUDA graph of one forward
     def _use_cuda_graph(self, dev):
         import os
@@ -606,7 +605,8 @@ class BERT(nn.Module):
         v = 0
         for p in self.parameters():
             v = (v * 1000003 + p._version * 31 + p.data_ptr()) & 0xFFFFFFFFFFFF
-        return v
+        from . import _lib
+        return (v, _lib.weights_epoch())
 
     def _forward_graph(self, nb, dev):
         """dict(graph, x [nb,S,D], ids [nb,Ttot], logits [nb,Ttot,1024]): target-embedding gather -> transformer ->

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 
 
 class AxialPositionalEmbedding(nn.Module):
@@ -31,7 +31,7 @@ class AxialPositionalEmbedding(nn.Module):
     def table(self):
         """float32 [max_seq_len, dim] on the parameters' device (cached until a parameter changes)."""
         ws = self.axis_weights()
-        key = tuple((w.data_ptr(), w._version) for w in ws)
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (_lib.weights_epoch(),)
         if self._cache is None or self._cache[0] != key:
             with torch.no_grad():
                 self._cache = (key, ops.axial_table([w.detach() for w in ws], self.shape))

@@ -60,6 +60,8 @@ def embed_gather(out, segments):
         e.ids, e.ids_bstride, e.n, e.seq_off = ids.data_ptr(), bstride, ids.shape[1], s["seq_off"]
         e.table = _req(s["table"], torch.float32, "table").data_ptr()
         assert s["table"].is_contiguous() and s["table"].shape[1] == D
+        e.table_rows = s["table"].shape[0]
+        assert s.get("table2") is None or s["table2"].shape[0] >= e.table_rows
         e.table2 = s["table2"].data_ptr() if s.get("table2") is not None else None
         e.pos = s["pos"].data_ptr() if s.get("pos") is not None else None
         if s.get("pos") is not None:
@@ -278,8 +280,9 @@ def vq_argmin(z_rows, codebook):
     assert z_rows.is_contiguous() and codebook.is_contiguous()
     T, dim = z_rows.shape
     idx = torch.empty(T, device=z_rows.device, dtype=torch.int64)
-    L.check(lib.mmvid_vq_argmin(_ptr(z_rows), _ptr(codebook), _ptr(idx), T, codebook.shape[0], dim, _stream()),
-            "vq_argmin")
+    e2 = torch.empty(codebook.shape[0], device=z_rows.device, dtype=torch.float32)  # stream-ordered scratch
+    L.check(lib.mmvid_vq_argmin(_ptr(z_rows), _ptr(codebook), _ptr(idx), _ptr(e2), T, codebook.shape[0], dim,
+                                _stream()), "vq_argmin")
     return idx
 
 

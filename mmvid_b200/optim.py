@@ -51,8 +51,11 @@ class _TensorTable:
         self.skipped = [0] * len(self.params)
 
     def refresh(self):
-        """Re-upload the table when any .grad pointer changed (zero_grad(set_to_none=True) reallocates them)."""
-        ptrs = tuple(0 if p.grad is None else p.grad.data_ptr() for p in self.params) + tuple(self.skipped)
+        """Re-upload the table when any pointer in it changed: .grad (zero_grad(set_to_none=True) reallocates them), a
+        replaced p.data, or replaced state tensors."""
+        ptrs = tuple(0 if p.grad is None else p.grad.data_ptr() for p in self.params) + tuple(self.skipped) \
+            + tuple(p.data_ptr() for p in self.params) \
+            + (() if self.ms is None else tuple(t.data_ptr() for t in self.ms) + tuple(t.data_ptr() for t in self.vs))
         if ptrs == self._grad_ptrs:
             return
         for i, p in enumerate(self.params):
@@ -150,6 +153,8 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             L.check(lib.mmvid_adam_step(*tab.args(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                         float(group["weight_decay"]), int(self.decoupled), step, ops._stream()), "adam_step")
+            # the kernel wrote the parameters through raw pointers: torch's version counters did not move
+            L.bump_weights_epoch()
         return loss
 
 

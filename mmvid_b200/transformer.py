@@ -17,7 +17,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 from ._lib import ACT_QUICKGELU, BF16, FP32, MASK_CAUSAL, MASK_NONE, MASK_PREV, TF32, PRECISIONS
 
 
@@ -47,7 +47,7 @@ class _Bf16Cache:
 
     def get(self, p):
         key = id(p)
-        tag = (p.data_ptr(), p._version)
+        tag = (p.data_ptr(), p._version, _lib.weights_epoch())
         hit = self._d.get(key)
         if hit is None or hit[0] != tag:
             hit = (tag, p.detach().to(torch.bfloat16).contiguous())

@@ -16,7 +16,7 @@ import math
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 from ._lib import FP32, MASK_NONE, PRECISIONS, TF32
 
 # mmvid_pytorch/data/vqgan.1024.config.yml:5-21 (the only VQGAN configuration MMVID ships)
@@ -151,7 +151,7 @@ class _PackCache:
         self._d = {}
 
     def conv(self, p):
-        tag = (p.data_ptr(), p._version)
+        tag = (p.data_ptr(), p._version, _lib.weights_epoch())
         hit = self._d.get(id(p))
         if hit is None or hit[0] != tag:
             hit = (tag, p.detach().permute(0, 2, 3, 1).contiguous())
@@ -159,7 +159,7 @@ class _PackCache:
         return hit[1]
 
     def cat(self, key, params):
-        tag = tuple((p.data_ptr(), p._version) for p in params)
+        tag = tuple((p.data_ptr(), p._version) for p in params) + (_lib.weights_epoch(),)
         hit = self._d.get(key)
         if hit is None or hit[0] != tag:
             hit = (tag, torch.cat([p.detach().reshape(p.shape[0], -1) if p.dim() > 1 else p.detach() for p in params], 0)

@@ -143,3 +143,56 @@ def test_fused_adam_and_clip_match_torch_optimisers(kind, wd):
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}  # torch's checkpoint layout (train.py:352)
     o_ref.load_state_dict({"state": {k: {kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}
                                      for k, v in sd["state"].items()}, "param_groups": sd["param_groups"]})
+
+
+def test_sampling_after_a_fused_adam_step_uses_the_updated_weights():
+    """FusedAdam writes parameters through raw pointers (no torch version bump): the axial position tables, 16-bit weight
+    copies and the captured CUDA graph must still follow.  Sample, take one large step, sample again, and compare with a
+    FRESH model loaded from the trained state dict (train.py samples periodically during training)."""
+    import random
+    from mmvid_b200 import optim as FO
+    cfg = BERT_CASES["bert_tiny"]
+    model, _ = build_bert(cfg, precision="tf32", sampling_mode="batched")
+    B = 2
+    text = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], 1).cuda()
+    visual = synth.synth_frames(B, cfg["num_visuals"], cfg["image_size"], 2).cuda()
+    frames = synth.synth_frames(B, cfg["num_targets"], cfg["image_size"], 3).cuda()
+
+    def sample(m):
+        torch.manual_seed(11)
+        with torch.no_grad():
+            return m.generate_images(text, visual=visual, mask_predict_steps=3, dynamic=False)[2]
+
+    def logits_of(m):
+        with torch.no_grad():
+            control = m(text, visual=visual, return_loss=False)
+            x = torch.zeros(B, m.total_seq_len, cfg["dim"], device="cuda")
+            x[:, :control.shape[1]] = control
+            from mmvid_b200 import ops
+            ids = torch.full((B, m.target_seq_len), 7, dtype=torch.long, device="cuda")
+            ops.embed_gather(x, [m._target_segment(ids)])
+            return m.transformer_forward(x).clone()
+
+    model.eval()
+    seq0, h0 = sample(model), logits_of(model)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = FO.FusedAdam(params, lr=0.05)
+    np.random.seed(1); random.seed(1); torch.manual_seed(1)
+    losses = model(text, visual=visual, target=frames, return_loss=True, rel=True, vid=True,
+                   msm_strategy_prob=np.array([0.7, 0.1, 0.1, 0.1]), msm_bernoulli_prob=[0.2, 0.5],
+                   vid_strategy_prob=np.array([0.25] * 4))
+    opt.zero_grad()
+    (7 * losses[0] + 0.5 * losses[1] + 0.5 * losses[2]).backward()
+    opt.step()
+    model.eval()
+    seq1, h1 = sample(model), logits_of(model)
+    fresh, _ = build_bert(cfg, precision="tf32", sampling_mode="batched")
+    fresh.load_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()})
+    fresh.eval()
+    seq2, h2 = sample(fresh), logits_of(fresh)
+    assert relerr(h1, h0) > 1e-2, "the step was too small to tell stale weights from fresh ones"
+    assert relerr(h1, h2) < 1e-6, "hidden states after the step differ from a fresh model with the same weights"
+    assert torch.equal(seq1, seq2)
+    print(f"after one FusedAdam step: hidden relerr vs before {relerr(h1, h0):.2e}, vs fresh model {relerr(h1, h2):.1e}; "
+          f"{int((seq1 != seq0).sum())} of {seq1.numel()} sampled ids changed")

@@ -396,24 +396,22 @@ def test_fused_qkv_on_the_cta_pair_kernel_is_identical_to_the_single_cta_kernel(
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
-@pytest.mark.parametrize("impl,poly", [("2", "0"), ("3", "2"), ("4", "0"), ("4", "2")])
-def test_attention_kernel_generations_agree(monkeypatch, prec, impl, poly):
-    """v4 (P over S in place), v5 (rotating score buffers, the default) with FMA-pipe exponentials, v6 (persistent: 180
-    items for 148 CTAs, so some CTAs walk two items and the causal items have different lengths): all against the fp64
-    reference with both masks."""
+@pytest.mark.parametrize("poly", ["0", "2", "4"])
+def test_attention_fma_pipe_exponentials_agree_with_fp64(monkeypatch, prec, poly):
+    """The rotating-score-buffer kernel with 0 / 2 / 4 of every 8 exponentials on the FMA pipe (MMVID_ATT_POLY), both masks,
+    causal items of different lengths, against the fp64 reference."""
     ops = _ops()
     from oracle import mmvid_oracle as O
     B, S, H = 6, 1100, 6
     g = torch.Generator().manual_seed(S)
     qkv = torch.randn(B * S, 3 * H * 64, generator=g).cuda()
-    monkeypatch.setenv("MMVID_ATT_IMPL", impl)
     monkeypatch.setenv("MMVID_ATT_POLY", poly)
     odt = torch.bfloat16 if prec == "bf16" else torch.float32
     for kind, mk, rows in (("mask_prev", ops.MASK_PREV, (400, 401)), ("causal", ops.MASK_CAUSAL, ())):
         mask = O.build_attention_mask(S, kind, rows) if kind == "mask_prev" else O.build_attention_mask(S, "causal")
         ref = _attn_ref(qkv, B, S, H, mask)
         out = ops.attention_tc(qkv, B, S, H, mk, rows, prec, out_dtype=odt).float()
-        assert relerr(out, ref) < TOL[prec], f"{prec} impl {impl} poly {poly} {kind}"
+        assert relerr(out, ref) < TOL[prec], f"{prec} poly {poly} {kind}"
 
 
 def test_groupnorm_streaming_kernel_exact_and_fast_swish():

@@ -164,7 +164,7 @@ def test_gemm_tile_picker_on_the_benchmark_shapes():
 
 
 def test_fma_pipe_exp2_polynomial_accuracy_claims():
-    """Bit-level numpy restatement of exp2_poly2 (tc_attention3.cu): clamp at -126, round-to-nearest through the 1.5 * 2^23
+    """Bit-level numpy restatement of exp2_poly2 (tc_attention.cu): clamp at -126, round-to-nearest through the 1.5 * 2^23
     magic constant, minimax polynomial on [-0.5, 0.5], exponent added as an integer.  Pins the accuracy the kernel's header
     claims (degree 4: 2.7e-6 for the tf32 path, degree 3: 7.5e-5 for the bf16 path) and the behaviour at the edges."""
     import numpy as np
