@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="A", choices=list(SHAPES))
     ap.add_argument("--batch", type=int, default=4, help="prompts per GPU per step")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp16", "bf16", "fp32"])
     ap.add_argument("--mp-steps", type=int, default=20)
     ap.add_argument("--vae-precision", default=None, choices=["tf32", "fp32"],
                     help="VQGAN conv precision (default: tf32 tensor cores unless --precision fp32)")
@@ -243,8 +243,8 @@ def build_artv(args, device):
 def build_model(args, device):
     if args.workload == "artv":
         return build_artv(args, device)
-    if args.workload == "train" and args.precision == "bf16":
-        raise SystemExit("training runs the tf32 or fp32 path (bf16 activations are an inference-only mode)")
+    if args.workload == "train" and args.precision in ("bf16", "fp16"):
+        raise SystemExit("training runs the tf32 or fp32 path (16-bit activations are an inference-only mode)")
     from mmvid_b200.dalle_bert import BERT
     from mmvid_b200.vae import VQGanVAE1024
     cfg = SHAPES[args.shape]
@@ -269,11 +269,11 @@ def build_model(args, device):
 def kernel_roofline(model, args, peaks, S, B):
     """Times the dominant kernels alone at the benchmark shapes with CUDA events on the launching stream."""
     from mmvid_b200 import ops
-    from mmvid_b200._lib import PRECISIONS, BF16
+    from mmvid_b200._lib import PRECISIONS
     prec = PRECISIONS[args.precision]
     dev = next(model.parameters()).device
     H = DIM // 64
-    act_dt = torch.bfloat16 if prec == BF16 else torch.float32
+    act_dt = ops.act_dtype(prec)
     qkv = torch.randn(B * S, 3 * DIM, device=dev)
     x = torch.randn(B * S, DIM, device=dev).to(act_dt)
     blk = model.transformer.transformer.resblocks[0]
@@ -301,7 +301,7 @@ def kernel_roofline(model, args, peaks, S, B):
         import ctypes as C
         from mmvid_b200 import _lib as L
         lib = L.load()
-        dt = torch.float32 if prec == 1 else torch.bfloat16
+        dt = act_dt
         q = torch.empty(B, H, S_pad, 64, device=dev, dtype=dt)
         k = torch.empty_like(q)
         vt = torch.empty(B, H, 64, S_pad, device=dev, dtype=dt)
@@ -469,7 +469,8 @@ def run_ours(args):
                        "train": "video-tokens/sec (BERT training step: forward + backward + clip + Adam)"}[args.workload],
             "value": value, "unit": "video-tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"tf32": "tf32 (fp32 storage, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
+            "dtype": {"tf32": "tf32 (fp32 storage, fp32 accumulate)", "bf16": "bf16 (fp32 accumulate, fp32 residual stream)",
+                      "fp16": "fp16 (fp32 accumulate, fp32 residual stream)", "fp32": "f32"}[args.precision],
             "data": "synthetic", "config": dict(workload_config(args, B), **({"workload": "DALLE(ART-V).generate_images with KV cache, shape " + args.shape + ": prefix 1+L+n, " + str(tokens_per_sample) + " decode steps, batch " + str(B)} if args.workload == "artv" else {})),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "video-tokens/s", "h2d_bytes_per_step": h2d_bytes,

@@ -15,7 +15,10 @@
  *   - activations are fp32 unless a dtype argument says otherwise; `precision` selects the math pipe:
  *       MMVID_FP32  CUDA-core FFMA, fp32 accumulate  (parity / bit-exact-index mode)
  *       MMVID_TF32  tcgen05.mma kind::tf32, fp32 accumulate in TMEM (<=1e-3 logits parity mode)
- *       MMVID_BF16  tcgen05.mma kind::f16 (bf16 operands), fp32 accumulate in TMEM (throughput mode)
+ *       MMVID_BF16  tcgen05.mma kind::f16 (bf16 operands), fp32 accumulate in TMEM (wide-range 16-bit mode; 8-bit mantissa)
+ *       MMVID_F16   tcgen05.mma kind::f16 (fp16 operands: the SAME 10-bit mantissa as tf32 at twice its rate and half its
+ *                   bytes), fp32 accumulate in TMEM; 16-bit stores saturate at +-65504 (default throughput mode)
+ *   16-bit tensors carry MMVID_DT_BF16 or MMVID_DT_F16; operand dtypes must match the precision.
  */
 #ifndef MMVID_B200_H
 #define MMVID_B200_H
@@ -30,10 +33,10 @@ extern "C" {
 typedef void* mmvid_stream_t; /* cudaStream_t */
 
 enum { MMVID_OK = 0, MMVID_EINVAL = -1, MMVID_ECUDA = -2, MMVID_EUNSUPPORTED = -3 };
-enum { MMVID_FP32 = 0, MMVID_TF32 = 1, MMVID_BF16 = 2 };
+enum { MMVID_FP32 = 0, MMVID_TF32 = 1, MMVID_BF16 = 2, MMVID_F16 = 3 };
 enum { MMVID_ACT_NONE = 0, MMVID_ACT_QUICKGELU = 1, MMVID_ACT_SWISH = 2 };
 enum { MMVID_MASK_NONE = 0, MMVID_MASK_CAUSAL = 1, MMVID_MASK_PREV = 2 };
-enum { MMVID_DT_F32 = 0, MMVID_DT_BF16 = 1 };
+enum { MMVID_DT_F32 = 0, MMVID_DT_BF16 = 1, MMVID_DT_F16 = 2 };
 
 int mmvid_version(void);
 const char* mmvid_last_error(void);

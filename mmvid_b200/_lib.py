@@ -8,11 +8,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmmvid_b200.so")
 
-FP32, TF32, BF16 = 0, 1, 2
+FP32, TF32, BF16, F16 = 0, 1, 2, 3
 ACT_NONE, ACT_QUICKGELU, ACT_SWISH = 0, 1, 2
 MASK_NONE, MASK_CAUSAL, MASK_PREV = 0, 1, 2
-DT_F32, DT_BF16 = 0, 1
-PRECISIONS = {"fp32": FP32, "tf32": TF32, "bf16": BF16}
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+PRECISIONS = {"fp32": FP32, "tf32": TF32, "bf16": BF16, "fp16": F16}
+H16 = (BF16, F16)  # kind::f16 precisions: 16-bit operands and activations, fp32 accumulation / residual stream
 
 _p, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 

@@ -2,6 +2,8 @@
 // QKV split/transposes, GroupNorm+swish (K11), VQ argmin (K14), codebook gather (K15), layout helpers.
 // All are coalesced along the channel (innermost) dimension with 128-bit accesses where alignment allows.
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <type_traits>
 
 namespace mmvid {
 thread_local char g_err[512] = "";
@@ -138,10 +140,14 @@ __global__ void layernorm_warp_kernel(const float* __restrict__ x, long long ldx
       if constexpr (sizeof(OutT) == 4) {
         reinterpret_cast<float4*>(out + row * (long long)D)[c] = o;
       } else {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        uint2 pk;  // 16-bit outputs saturate instead of overflowing to inf (fp16: +-65504)
+        if constexpr (std::is_same<OutT, __half>::value) {
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
+        } else {
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
+        }
         reinterpret_cast<uint2*>(out + row * (long long)D)[c] = pk;
       }
     }
@@ -157,6 +163,8 @@ extern "C" int mmvid_layernorm(const float* x, long long ldx, const float* gamma
   cudaStream_t st = to_stream(stream);
   if (out_dtype == MMVID_DT_F32)
     layernorm_warp_kernel<8, float><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (float*)out, rows, D, eps);
+  else if (out_dtype == MMVID_DT_F16)
+    layernorm_warp_kernel<8, __half><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__half*)out, rows, D, eps);
   else
     layernorm_warp_kernel<8, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__nv_bfloat16*)out, rows,
                                                                       D, eps);
@@ -233,6 +241,7 @@ template <typename T>
 __device__ __forceinline__ T cvt_out(float v);
 template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
 
 template <typename T>
 __global__ void qkv_split_kernel(const float* __restrict__ qkv, T* __restrict__ q, T* __restrict__ k,
@@ -263,6 +272,8 @@ extern "C" int mmvid_qkv_split(const float* qkv, void* q, void* k, void* vt, int
   dim3 grid(S_pad / 64, H, B);
   if (dtype == MMVID_DT_F32)
     qkv_split_kernel<float><<<grid, 256, 0, to_stream(stream)>>>(qkv, (float*)q, (float*)k, (float*)vt, H, S, S_pad);
+  else if (dtype == MMVID_DT_F16)
+    qkv_split_kernel<__half><<<grid, 256, 0, to_stream(stream)>>>(qkv, (__half*)q, (__half*)k, (__half*)vt, H, S, S_pad);
   else
     qkv_split_kernel<__nv_bfloat16><<<grid, 256, 0, to_stream(stream)>>>(qkv, (__nv_bfloat16*)q, (__nv_bfloat16*)k,
                                                                         (__nv_bfloat16*)vt, H, S, S_pad);

@@ -100,7 +100,7 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& e0, float&
 
 struct Att3Args {
   unsigned long long* trace;  // debug timeline (mmvid_debug_attention_trace), normally null
-  void* out; long long ldo; int out_bf16;
+  void* out; long long ldo; int out_h16;  // 1: 16-bit output in the kernel's own 16-bit flavour (bf16 | fp16)
   int B, H, S, S_pad, mask_kind;
   int prev_rows[4]; int n_prev;
   int spin;  // 1: the MMA threads poll p_ready with test_wait instead of try_wait
@@ -118,7 +118,9 @@ constexpr size_t att3_smem_bytes() {
   return (size_t)6 * (TF32 ? 32768 : 16384) + 1024 + 512;
 }
 
-template <bool TF32, int POLY8>
+// F16 (16-bit kinds only): fp16 operands / P / 16-bit output instead of bf16 - the tf32 mantissa at the kind::f16 rate.
+// P <= 2^8 (lazy rescale) and softmax inputs of O(10) sit comfortably inside the fp16 range.
+template <bool TF32, int POLY8, bool F16 = false>
 __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                        const __grid_constant__ CUtensorMap tmK,
                                                                        const __grid_constant__ CUtensorMap tmV, Att3Args a) {
@@ -216,8 +218,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
     const int my = a.dual ? (warp == 3 ? 1 : 0) : 0;
     const int stride = a.dual ? 2 : 1;
     if ((a.dual || warp == 1) && elect_one()) {
-      constexpr uint32_t idesc_qk = make_idesc<TF32>(BQ, BKV);
-      constexpr uint32_t idesc_pv = make_idesc<TF32>(BQ, HD);
+      constexpr uint32_t idesc_qk = TF32 ? make_idesc<true>(BQ, BKV) : make_idesc_h16(F16, BQ, BKV);
+      constexpr uint32_t idesc_pv = TF32 ? make_idesc<true>(BQ, HD) : make_idesc_h16(F16, BQ, HD);
       constexpr uint32_t TB16 = T_BYTES >> 4;  // descriptor address units (16 B) per tile
       // all shared-memory descriptors are  base + small multiples: the address field cannot carry (smem < 256 KB)
       const uint64_t dQ0 = make_smem_desc_sw128(smem_u32(sQ(0)));
@@ -419,8 +421,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
           if constexpr (TF32) {
             r[ch][i] = __float_as_uint(e0); r[ch][i + 1] = __float_as_uint(e1);
           } else {
-            __nv_bfloat162 v2 = __floats2bfloat162_rn(e0, e1);
-            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&v2);
+            pk[i >> 1] = pack_h16<F16>(e0, e1);
           }
         }
         if constexpr (TF32) tmem_st32(t_s + ch * 32, r[ch]);
@@ -456,19 +457,19 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
     const float inv = 1.f / l;
     uint8_t* stage_base = g == 0 ? sK(0) : sV(0);  // 2 contiguous tiles each: >= 128 x 68 floats
     const int q_tile0 = q0 + g * BQ;
-    if (a.out_bf16) {
+    if (a.out_h16) {
       constexpr int LD = HD + 8;
-      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage_base) + (size_t)row_local * LD;
+      uint16_t* st = reinterpret_cast<uint16_t*>(stage_base) + (size_t)row_local * LD;
 #pragma unroll
       for (int i = 0; i < HD; i += 2)
-        *reinterpret_cast<__nv_bfloat162*>(st + i) = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv);
+        *reinterpret_cast<uint32_t*>(st + i) = pack_h16<F16>(o[i] * inv, o[i + 1] * inv);
       __syncwarp();
-      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+      uint16_t* outp = reinterpret_cast<uint16_t*>(a.out);
       for (int r0 = 0; r0 < 32; r0 += 4) {
         const int rl = qd * 32 + r0 + (lane >> 3);
         const int s = q_tile0 + rl;
         if (s < a.S) {
-          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<__nv_bfloat16*>(stage_base) + (size_t)rl * LD + (lane & 7) * 8);
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<uint16_t*>(stage_base) + (size_t)rl * LD + (lane & 7) * 8);
           *reinterpret_cast<uint4*>(outp + ((long long)b * a.S + s) * a.ldo + h * HD + (lane & 7) * 8) = v;
         }
       }
@@ -497,26 +498,26 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-template <bool TF32, int POLY8>
+template <bool TF32, int POLY8, bool F16>
 int launch_att3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Att3Args& a, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = att3_smem_bytes<TF32>();
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(attention_tc3_kernel<TF32, POLY8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(attention_tc3_kernel<TF32, POLY8, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(attention_tc3): %s", cudaGetErrorString(err));
     attr_set = true;
   }
   dim3 grid((a.S_pad / BQ + 1) / 2, a.B * a.H);
-  attention_tc3_kernel<TF32, POLY8><<<grid, ATT3_THREADS, smem, st>>>(tq, tk, tv, a);
+  attention_tc3_kernel<TF32, POLY8, F16><<<grid, ATT3_THREADS, smem, st>>>(tq, tk, tv, a);
   return check_launch("attention_tc3");
 }
 
-template <bool TF32>
+template <bool TF32, bool F16>
 int launch_att3_poly(int poly8, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Att3Args& a,
                      cudaStream_t st) {
-  if (poly8 == 0) return launch_att3<TF32, 0>(tq, tk, tv, a, st);
-  if (poly8 == 2) return launch_att3<TF32, 2>(tq, tk, tv, a, st);
-  if (poly8 == 4) return launch_att3<TF32, 4>(tq, tk, tv, a, st);
+  if (poly8 == 0) return launch_att3<TF32, 0, F16>(tq, tk, tv, a, st);
+  if (poly8 == 2) return launch_att3<TF32, 2, F16>(tq, tk, tv, a, st);
+  if (poly8 == 4) return launch_att3<TF32, 4, F16>(tq, tk, tv, a, st);
   return fail(MMVID_EINVAL, "attention_tc3: poly8 must be 0, 2 or 4%s", "");
 }
 
@@ -524,17 +525,20 @@ int launch_att3_poly(int poly8, const CUtensorMap& tq, const CUtensorMap& tk, co
 
 // Rotating-score-buffer kernel.  poly8: how many of every 8 exponentials run on the FMA pipe (0, 2, 4); spin: the
 // MMA thread polls p_ready.  trace: see mmvid_debug_attention_trace below.
-extern "C" int mmvid_attention_v5(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
-                                  int out_bf16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
-                                  const int* host_prev_rows, int n_prev, int tf32, int poly8, int spin, int dual,
-                                  int pingpong, unsigned long long* trace, cudaStream_t st) {
+// kind: MMVID_TF32 | MMVID_BF16 | MMVID_F16
+static int mmvid_attention_v5(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
+                              int out_h16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
+                              const int* host_prev_rows, int n_prev, int kind, int poly8, int spin, int dual,
+                              int pingpong, unsigned long long* trace, cudaStream_t st) {
   Att3Args a{};
   a.trace = trace;
-  a.out = out; a.ldo = ldo; a.out_bf16 = out_bf16;
+  a.out = out; a.ldo = ldo; a.out_h16 = out_h16;
   a.B = B; a.H = H; a.S = S; a.S_pad = S_pad; a.mask_kind = mask_kind; a.n_prev = n_prev;
   a.spin = spin; a.dual = dual; a.pingpong = pingpong;
   for (int i = 0; i < n_prev; ++i) a.prev_rows[i] = host_prev_rows[i];
-  return tf32 ? launch_att3_poly<true>(poly8, *tq, *tk, *tv, a, st) : launch_att3_poly<false>(poly8, *tq, *tk, *tv, a, st);
+  if (kind == MMVID_TF32) return launch_att3_poly<true, false>(poly8, *tq, *tk, *tv, a, st);
+  if (kind == MMVID_F16) return launch_att3_poly<false, true>(poly8, *tq, *tk, *tv, a, st);
+  return launch_att3_poly<false, false>(poly8, *tq, *tk, *tv, a, st);
 }
 
 namespace mmvid { unsigned long long* g_att_trace = nullptr; }
@@ -557,12 +561,14 @@ int env_int(const char* name, int dflt) {
 extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, void* out, int out_dtype, long long ldo,
                                int B, int H, int S, int S_pad, int mask_kind, const int* host_prev_rows, int n_prev,
                                int precision, mmvid_stream_t stream) {
-  MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16, "tensor-core attention needs TF32 or BF16");
+  MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16 || precision == MMVID_F16,
+                "tensor-core attention needs TF32, BF16 or F16");
   MMVID_REQUIRE(S_pad % 128 == 0 && S_pad >= S && S > 0, "S_pad multiple of 128");
   MMVID_REQUIRE(n_prev >= 0 && n_prev <= 4, "at most 4 mask_prev rows");
   MMVID_REQUIRE((long long)B * H <= 65535, "B*H <= 65535");
   const bool tf32 = precision == MMVID_TF32;
-  const int esz = tf32 ? 4 : 2, dt = tf32 ? MMVID_DT_F32 : MMVID_DT_BF16;
+  const int esz = tf32 ? 4 : 2, dt = tf32 ? MMVID_DT_F32 : (precision == MMVID_F16 ? MMVID_DT_F16 : MMVID_DT_BF16);
+  MMVID_REQUIRE(out_dtype == MMVID_DT_F32 || (!tf32 && out_dtype == dt), "output: fp32 or the precision's own 16-bit type");
   const uint32_t BKE = 128 / esz;
   CUtensorMap tq, tk, tv;
   {
@@ -584,8 +590,8 @@ extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, voi
   // Measured defaults (profiles/r1_f_attention_v5.md): tf32 keeps every exponential on MUFU, the 16-bit kinds move 2 of 8
   // to the FMA pipe.  MMVID_ATT_POLY (0|2|4 of every 8 exponentials on the FMA pipe), MMVID_ATT_PP (0|1 MUFU ping-pong
   // token), MMVID_ATT_SPIN (0|1) and MMVID_ATT_DUAL (0|1: one or two MMA-issuing threads) are tuning switches.
-  return mmvid_attention_v5(&tq, &tk, &tv, out, out_dtype == MMVID_DT_BF16, ldo, B, H, S, S_pad, mask_kind, host_prev_rows,
-                            n_prev, tf32 ? 1 : 0, env_int("MMVID_ATT_POLY", tf32 ? 0 : 2), env_int("MMVID_ATT_SPIN", 0),
+  return mmvid_attention_v5(&tq, &tk, &tv, out, out_dtype != MMVID_DT_F32, ldo, B, H, S, S_pad, mask_kind, host_prev_rows,
+                            n_prev, precision, env_int("MMVID_ATT_POLY", tf32 ? 0 : 2), env_int("MMVID_ATT_SPIN", 0),
                             env_int("MMVID_ATT_DUAL", 1), env_int("MMVID_ATT_PP", 0), mmvid::g_att_trace,
                             to_stream(stream));
 }

@@ -234,12 +234,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 // advance along K inside the 128-byte swizzle atom: +bytes (must stay < 128)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, K-major A and B
-template <bool TF32>
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N) {
-  const uint32_t fmt = TF32 ? 2u : 1u;  // F16F32Format: BF16 = 1, TF32 = 2
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, K-major A and B.
+// a/b format field (F16F32Format): F16 = 0, BF16 = 1, TF32 = 2.
+__host__ __device__ constexpr uint32_t make_idesc_fmt(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+template <bool TF32>
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N) { return make_idesc_fmt(TF32 ? 2u : 1u, M, N); }
+// kind::f16 with fp16 operands (same 10-bit mantissa as tf32 at twice the rate) when f16 != 0, else bf16
+__host__ __device__ constexpr uint32_t make_idesc_h16(bool f16, uint32_t M, uint32_t N) { return make_idesc_fmt(f16 ? 0u : 1u, M, N); }
+
+// two floats -> one packed 16-bit pair (lo in the low half = the lower address), round to nearest, overflow saturates to
+// the largest finite value instead of inf (an inf operand would turn a whole MMA row into NaN)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h16(float lo, float hi) {
+  uint32_t r;
+  if constexpr (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_h16_rt(float lo, float hi, int f16) { return f16 ? pack_h16<true>(lo, hi) : pack_h16<false>(lo, hi); }
+__device__ __forceinline__ uint16_t cvt_h16_rt(float v, int f16) { return (uint16_t)(pack_h16_rt(v, 0.f, f16) & 0xffffu); }
 
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -1,4 +1,4 @@
-// tcgen05 GEMM for every Linear / 1x1 conv of the hot path (MMVID_TF32 and MMVID_BF16 precision):
+// tcgen05 GEMM for every Linear / 1x1 conv of the hot path (MMVID_TF32, MMVID_BF16 and MMVID_F16 precision):
 //     C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual)
 // Persistent and warp-specialised: one CTA per SM walks 128 x BN output tiles (BN = 256 / 128 / 64):
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> 4..8-stage smem ring, mbarrier full/empty
@@ -11,6 +11,7 @@
 // to tf32 inside the TMA unit); M/N/K tails rely on TMA zero fill, stores are predicated.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 #include <mutex>
 #include <stdlib.h>
@@ -48,6 +49,7 @@ int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, con
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   // loads of fp32 operands use TFLOAT32 (round-to-nearest in the TMA unit); DT_F32_EXACT is for stores of fp32 results
   const CUtensorMapDataType dt = dtype == MMVID_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : dtype == MMVID_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                  : (dtype == DT_F32_EXACT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -71,16 +73,17 @@ struct EpiArgs {
   long long ldr;
   void* C;
   long long ldc;
-  int c_bf16;
+  int c_h16;   // result type: 0 = fp32, 1 = bf16, 2 = fp16
+  int op_f16;  // 16-bit kinds: operands are fp16 (1) or bf16 (0)
   long long M;
   int N, K, act;
   // implicit-GEMM conv (CONV=true): 128-pixel M tile = box {BW, BH, BNI} of the NHWC input, K = (tap, channel block)
   int cCin, cKW, cPadT, cPadL, cBW, cBH, cBNI, cW, cH;
   int num_m_tiles, num_n_tiles;
   // QKV mode (qkv_q != nullptr): the [M, 3*H*64] result is scattered straight into the attention layout
-  //   Q,K -> [B,H,S_pad,64]   V -> V^T [B,H,64,S_pad]   (fp32 or bf16 via c_bf16); bias applied, no act/residual
+  //   Q,K -> [B,H,S_pad,64]   V -> V^T [B,H,64,S_pad]   (fp32 or 16-bit via c_h16); bias applied, no act/residual
   void* qkv_q; void* qkv_k; void* qkv_vt; int qS, qSpad, qH;
-  int tma_store;  // 1: fp32 result tiles leave through TMA bulk stores (tmC), see the epilogue
+  int tma_store;  // 1: result tiles leave through TMA bulk stores (tmC; tmC1 for lone 16-bit chunks), see the epilogue
   unsigned long long* trace;  // debug timeline of CTA 0 (mmvid_debug_gemm_trace), normally null
   int spin;    // 1: the TMA / MMA threads poll their ring barriers (mbar_wait_spin) instead of suspending in try_wait
   int raster;  // 0: m fastest; 1: n fastest; 2: 8-wide n groups (each wave covers ~8 weight tiles x ~18 row tiles)
@@ -120,10 +123,12 @@ constexpr size_t gemm_smem_bytes() {
 // Persistent, warp-specialised tcgen05 GEMM.  grid = min(#tiles, #SMs); every CTA walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so concurrently running CTAs share the same weight
 // tile in L2).  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue), tile loop.
-template <bool TF32, int BN, bool CONV, bool SWAP = false>
+// H16: the TMA-store epilogue writes 16-bit results (compile-time so that the fp32 epilogue keeps its register budget)
+template <bool TF32, int BN, bool CONV, bool SWAP = false, bool H16 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
-                                                                 const __grid_constant__ CUtensorMap tmC, EpiArgs e) {
+                                                                 const __grid_constant__ CUtensorMap tmC,
+                                                                 const __grid_constant__ CUtensorMap tmC1, EpiArgs e) {
   constexpr int STAGES = gemm_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
   // carve: [barriers 256 B][pad to 1024][stages: A | B][epilogue staging]
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc<TF32>(BM, BN);
+      const uint32_t idesc = TF32 ? make_idesc<true>(BM, BN) : make_idesc_h16(e.op_f16 != 0, BM, BN);
       uint32_t it = 0, tile_iter = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
         const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
@@ -290,6 +295,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (etr) gemm_stamp(e, tile_iter, 9);
           }
+          // 16-bit results (H16): the group's chunks are packed and staged one after the other and leave together as one
+          // {64 x 32} box (128-byte rows); a lone chunk leaves as a {32 x 32} box (tc_epilogue.cuh)
+          const int n_grp0 = n0 + c0 * 32;
+          int nvalid = 0;
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc)
+            if (n_grp0 + cc * 32 < e.N) nvalid = cc + 1;
+          if (H16 && nvalid > 0) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
 #pragma unroll
           for (int cc = 0; cc < GRP; ++cc) {
             const int ncol = n0 + (c0 + cc) * 32;
@@ -344,27 +360,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 o[4 * i + 2] += res[cc][i].z; o[4 * i + 3] += res[cc][i].w;
               }
             }
+            if constexpr (H16) {
+              const bool f16 = e.c_h16 == 2;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t u0 = pack_h16_rt(o[8 * j + 0], o[8 * j + 1], f16), u1 = pack_h16_rt(o[8 * j + 2], o[8 * j + 3], f16);
+                const uint32_t u2 = pack_h16_rt(o[8 * j + 4], o[8 * j + 5], f16), u3 = pack_h16_rt(o[8 * j + 6], o[8 * j + 7], f16);
+                uint32_t addr;
+                if (nvalid == 2) addr = st_row + (uint32_t)(((cc * 4 + j) ^ (lane & 7)) * 16);
+                else { const uint32_t lin = (uint32_t)(lane * 64 + j * 16); addr = st_base + (lin ^ (((lin >> 7) & 7u) << 4)); }
+                sts128_u32(addr, u0, u1, u2, u3);
+              }
+              continue;
+            } else {
             // the previous chunk's bulk store must have finished READING the staging buffer
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (lane == 0) tma_store_wait_read();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)  // 16-byte unit j of row r lives at unit j ^ (r & 7): the TMA 128-byte swizzle
               sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tmC)),
-                           "r"(st_base), "r"(ncol), "r"(m0 + q * 32)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+            if (lane == 0) tma_store_2d(&tmC, st_base, ncol, m0 + q * 32);
+            }  // !H16
+          }
+          if (H16 && nvalid > 0) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(nvalid == 2 ? &tmC : &tmC1, st_base, n_grp0, m0 + q * 32);
           }
           if (!SWAP && e.residual && c0 + GRP < NCH) load_res(c0 + GRP);
         }
         if (etr) gemm_stamp(e, tile_iter, 10);
       }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores done before smem goes away
+      if (lane == 0) tma_store_wait_all();  // all stores done before smem goes away
       __syncwarp();
     } else {
     const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
@@ -447,12 +476,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               const int bb = (int)(m / e.qS), ss = (int)(m - (long long)bb * e.qS);
               const long long off = (((long long)bb * e.qH + hh) * e.qSpad + ss) * 64 + d0 + col;
               const float o0 = v.x + bias_r[c].x, o1 = v.y + bias_r[c].y, o2 = v.z + bias_r[c].z, o3 = v.w + bias_r[c].w;
-              if (e.c_bf16) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+              if (e.c_h16) {
                 uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + off) = pk;
+                pk.x = pack_h16_rt(o0, o1, e.c_h16 == 2);
+                pk.y = pack_h16_rt(o2, o3, e.c_h16 == 2);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dst) + off) = pk;
               } else {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + off) = make_float4(o0, o1, o2, o3);
               }
@@ -467,7 +495,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
               for (int d = 0; d < 32; ++d) {
                 const float o = __uint_as_float(r[d]) + (e.bias ? __ldg(e.bias + nc + d) : 0.f);
-                if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.qkv_vt)[base + (long long)d * e.qSpad] = __float2bfloat16_rn(o);
+                if (e.c_h16) reinterpret_cast<uint16_t*>(e.qkv_vt)[base + (long long)d * e.qSpad] = cvt_h16_rt(o, e.c_h16 == 2);
                 else reinterpret_cast<float*>(e.qkv_vt)[base + (long long)d * e.qSpad] = o;
               }
             }
@@ -495,12 +523,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
             if (e.residual) { o[0] += res[i].x; o[1] += res[i].y; o[2] += res[i].z; o[3] += res[i].w; }
             if (m < e.M && n_ok) {
-              if (e.c_bf16) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+              if (e.c_h16) {
                 uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + m * e.ldc + n) = pk;
+                pk.x = pack_h16_rt(o[0], o[1], e.c_h16 == 2);
+                pk.y = pack_h16_rt(o[2], o[3], e.c_h16 == 2);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.C) + m * e.ldc + n) = pk;
               } else {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
               }
@@ -518,7 +545,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               if (n + j >= e.N) break;
               float x = apply_act(o[j], e.act);
               if (e.residual) x += e.residual[m * e.ldr + n + j];
-              if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.C)[m * e.ldc + n + j] = __float2bfloat16_rn(x);
+              if (e.c_h16) reinterpret_cast<uint16_t*>(e.C)[m * e.ldc + n + j] = cvt_h16_rt(x, e.c_h16 == 2);
               else reinterpret_cast<float*>(e.C)[m * e.ldc + n + j] = x;
             }
           }
@@ -585,15 +612,22 @@ int pick_bn(long long M, int N, bool allow256 = true) {
   return best;
 }
 
-template <bool TF32, int BN, bool CONV = false, bool SWAP = false>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream_t st) {
+template <bool TF32, int BN, bool CONV, bool SWAP, bool H16>
+int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC1, const EpiArgs& e,
+             int grid, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = gemm_smem_bytes<BN>();
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN, CONV, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN, CONV, SWAP, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(err));
     attr_set = true;
   }
+  gemm_tc_kernel<TF32, BN, CONV, SWAP, H16><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC1, e);
+  return check_launch("gemm_tc");
+}
+
+template <bool TF32, int BN, bool CONV = false, bool SWAP = false>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream_t st) {
   e.num_m_tiles = (int)ceil_div<long long>(e.M, BM);
   e.num_n_tiles = ceil_div(e.N, BN);
   if (SWAP) {  // transposed conv tile: "m" tiles walk the output channels (128 each), "n" tiles the pixels (BN each)
@@ -604,23 +638,35 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream
   e.trace = g_gemm_trace;
   e.raster = env_int("MMVID_GEMM_RASTER", 1);  // n fastest: consecutive CTAs share the activation tile (measured best)
   // result tiles leave through TMA bulk stores when the output is plain row-major fp32 with 32-column granularity
-  CUtensorMap tmC = tmA;  // placeholder when unused
+  CUtensorMap tmC = tmA, tmC1 = tmA;  // placeholders when unused
   e.tma_store = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (env_int("MMVID_GEMM_TMA_STORE", GEMM_TMA_STORE_DEFAULT) && !e.c_bf16 && e.qkv_q == nullptr && e.N % 32 == 0 &&
-      e.ldc % 4 == 0 && al16(e.C) && (!e.residual || (e.ldr % 4 == 0 && al16(e.residual))) && (!e.bias || al16(e.bias))) {
+  const int csz = e.c_h16 ? 2 : 4;
+  if (env_int("MMVID_GEMM_TMA_STORE", GEMM_TMA_STORE_DEFAULT) && !((SWAP || CONV || TF32) && e.c_h16) && e.qkv_q == nullptr && e.N % 32 == 0 &&
+      (e.ldc * csz) % 16 == 0 && al16(e.C) && (!e.residual || (e.ldr % 4 == 0 && al16(e.residual))) && (!e.bias || al16(e.bias))) {
     uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
-    uint64_t str[1] = {(uint64_t)e.ldc * 4};
-    uint32_t box[2] = {32, 32};
-    int rc = make_tensor_map(&tmC, e.C, DT_F32_EXACT, 2, dims, str, box);
-    if (rc) return rc;
+    uint64_t str[1] = {(uint64_t)e.ldc * csz};
+    if (e.c_h16) {
+      const int dt = e.c_h16 == 2 ? MMVID_DT_F16 : MMVID_DT_BF16;
+      uint32_t box[2] = {64, 32}, box1[2] = {32, 32};
+      int rc = make_tensor_map(&tmC, e.C, dt, 2, dims, str, box);
+      if (rc) return rc;
+      rc = make_tensor_map(&tmC1, e.C, dt, 2, dims, str, box1);
+      if (rc) return rc;
+    } else {
+      uint32_t box[2] = {32, 32};
+      int rc = make_tensor_map(&tmC, e.C, DT_F32_EXACT, 2, dims, str, box);
+      if (rc) return rc;
+    }
     e.tma_store = 1;
   }
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   if (SWAP && !e.tma_store) return fail(MMVID_EINVAL, "transposed conv tile needs the TMA-store epilogue%s");
-  gemm_tc_kernel<TF32, BN, CONV, SWAP><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, e);
-  return check_launch("gemm_tc");
+  if constexpr (!TF32 && !CONV && !SWAP) {
+    if (e.c_h16 && e.tma_store) return launch_k<TF32, BN, CONV, SWAP, true>(tmA, tmB, tmC, tmC1, e, grid, st);
+  }
+  return launch_k<TF32, BN, CONV, SWAP, false>(tmA, tmB, tmC, tmC1, e, grid, st);
 }
 
 template <bool TF32, bool CONV>
@@ -637,7 +683,17 @@ namespace {
 // MMVID_GEMM_2CTA=128|192|256 forces it everywhere, =1 disables it.
 int pick_pair_bn(long long M, int N, int K, bool tf32, int c_dtype) {
   int bn2 = env_int("MMVID_GEMM_2CTA", 0);
-  if (bn2 == 0 && c_dtype == MMVID_DT_F32 && N >= 512 && M >= 1024) {
+  if (bn2 == 0 && !tf32 && N >= 512 && M >= 1024) {
+    // kind::f16: the MMAs take half the time for the same operand bytes, so the widest tile (fewest bytes per FLOP: the
+    // L2 -> SM stream is what bounds these GEMMs) wins unless it quantises badly over the 74 CTA pairs
+    const int sms = num_sms();
+    const long long mt2 = ceil_div<long long>(M, 2 * BM);
+    const double p128 = (double)ceil_div<long long>(mt2 * ceil_div(N, 128), sms / 2) * 128.0;
+    const double p192 = (double)ceil_div<long long>(mt2 * ceil_div(N, 192), sms / 2) * 180.0;
+    const double p256 = (double)ceil_div<long long>(mt2 * ceil_div(N, 256), sms / 2) * 230.0;
+    bn2 = (p256 <= p192 && p256 <= p128) ? 256 : (p192 <= p128 ? 192 : 128);
+  }
+  if (bn2 == 0 && tf32 && c_dtype == MMVID_DT_F32 && N >= 512 && M >= 1024) {
     // An SS tcgen05.mma costs ~100 clk whatever its N (r1q-r1v traces: 380-430 clk per 4-instruction k-block for N = 128,
     // 192 and 256 alike; the 128-row A slice fetch from shared memory is the floor), so only instructions with >= 100 clk
     // of work run the tensor pipe at its rate: 256 x 192 / 256 x 256 CTA-pair tiles.  With the TMA-store epilogue these
@@ -679,7 +735,7 @@ extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const
                                 long long ldc, long long M, int N, int K, int act, int precision, int BN, cudaStream_t st);
 
 extern "C" int mmvid_linear_qkv_tc2(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* q,
-                                    void* k, void* vt, int B, int H, int S, int S_pad, cudaStream_t st);
+                                    void* k, void* vt, int B, int H, int S, int S_pad, int precision, cudaStream_t st);
 
 namespace {
 struct QkvReq { void* q; void* k; void* vt; int S, Spad, H; };
@@ -690,9 +746,10 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
                                const float* bias, const float* residual, long long ldr, void* C, int c_dtype,
                                long long ldc, long long M, int N, int K, int act, int precision, cudaStream_t st) {
   const bool tf32 = precision == MMVID_TF32;
-  MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16, "precision");
-  const int want = tf32 ? MMVID_DT_F32 : MMVID_DT_BF16;
-  MMVID_REQUIRE(a_dtype == want && w_dtype == want, "operand dtype must match precision (fp32 for TF32, bf16 for BF16)");
+  MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16 || precision == MMVID_F16, "precision");
+  const int want = tf32 ? MMVID_DT_F32 : (precision == MMVID_F16 ? MMVID_DT_F16 : MMVID_DT_BF16);
+  MMVID_REQUIRE(a_dtype == want && w_dtype == want,
+                "operand dtype must match precision (fp32 for TF32, bf16 for BF16, fp16 for F16)");
   const int esz = tf32 ? 4 : 2;
   MMVID_REQUIRE((lda * esz) % 16 == 0 && (ldw * esz) % 16 == 0, "row strides must be multiples of 16 bytes");
   MMVID_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "16-byte alignment");
@@ -725,7 +782,9 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
     if (rc) return rc;
   }
   EpiArgs e{};
-  e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc; e.c_bf16 = c_dtype == MMVID_DT_BF16;
+  e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc;
+  e.c_h16 = c_dtype == MMVID_DT_BF16 ? 1 : (c_dtype == MMVID_DT_F16 ? 2 : 0);
+  e.op_f16 = precision == MMVID_F16;
   e.M = M; e.N = N; e.K = K; e.act = act;
   if (g_qkv.q) { e.qkv_q = g_qkv.q; e.qkv_k = g_qkv.k; e.qkv_vt = g_qkv.vt; e.qS = g_qkv.S; e.qSpad = g_qkv.Spad; e.qH = g_qkv.H; }
   return tf32 ? launch_bn<true, false>(BN, tmA, tmB, e, st) : launch_bn<false, false>(BN, tmA, tmB, e, st);
@@ -772,7 +831,7 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
         if (rc) return rc;
       }
       EpiArgs e{};
-      e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_bf16 = 0;
+      e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_h16 = 0; e.op_f16 = 0;
       e.M = M; e.N = p->Cout; e.K = K; e.act = MMVID_ACT_NONE;
       e.cCin = p->Cin; e.cKW = p->KW; e.cPadT = p->pad_t; e.cPadL = p->pad_l; e.cBW = BW2; e.cBH = BH2; e.cBNI = BNI2;
       e.cW = p->W; e.cH = p->H;
@@ -799,7 +858,7 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
     if (rc) return rc;
   }
   EpiArgs e{};
-  e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_bf16 = 0;
+  e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_h16 = 0; e.op_f16 = 0;
   e.M = M; e.N = p->Cout; e.K = K; e.act = MMVID_ACT_NONE;
   e.cCin = p->Cin; e.cKW = p->KW; e.cPadT = p->pad_t; e.cPadL = p->pad_l; e.cBW = BW; e.cBH = BH; e.cBNI = BNI;
   e.cW = p->W; e.cH = p->H;
@@ -813,12 +872,12 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
 extern "C" int mmvid_linear_qkv(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
                                 const float* bias, void* q, void* k, void* vt, int out_dtype, int B, int H, int S,
                                 int S_pad, int precision, mmvid_stream_t stream) {
-  MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16, "tensor-core precision required");
+  MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16 || precision == MMVID_F16, "tensor-core precision required");
   MMVID_REQUIRE(S_pad >= S && S_pad % 64 == 0, "S_pad");
-  if (precision == MMVID_TF32 && out_dtype == MMVID_DT_F32 && a_dtype == MMVID_DT_F32 && w_dtype == MMVID_DT_F32 &&
-      env_int("MMVID_QKV_PAIR", 1)) {
+  const int want = precision == MMVID_TF32 ? MMVID_DT_F32 : (precision == MMVID_F16 ? MMVID_DT_F16 : MMVID_DT_BF16);
+  if (out_dtype == want && a_dtype == want && w_dtype == want && env_int("MMVID_QKV_PAIR", 1)) {
     // 256 x 256 CTA-pair tiles with the TMA-store scatter (tc_gemm2.cu); 1 = preconditions not met, use the kernel below
-    const int rc = mmvid_linear_qkv_tc2(A, lda, W, ldw, bias, q, k, vt, B, H, S, S_pad, to_stream(stream));
+    const int rc = mmvid_linear_qkv_tc2(A, lda, W, ldw, bias, q, k, vt, B, H, S, S_pad, precision, to_stream(stream));
     if (rc != 1) return rc;
   }
   g_qkv = QkvReq{q, k, vt, S, S_pad, H};

@@ -9,6 +9,7 @@
 //   tmem_full[a] one per CTA (multicast commit);  tmem_empty[a] leader's barrier, 16 arrivals (8 warps x 2 CTAs)
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 #include <stdlib.h>
 
@@ -26,15 +27,17 @@ constexpr int EPI_LD = 32;
 
 struct Epi2Args {
   const float* bias; const float* residual; long long ldr;
-  void* C; long long ldc; int c_bf16;
+  void* C; long long ldc;
+  int c_h16;   // result type: 0 = fp32, 1 = bf16, 2 = fp16
+  int op_f16;  // 16-bit kinds: operands are fp16 (1) or bf16 (0)
   long long M; int N, K, act;
   int num_m_tiles /* 256-row tiles */, num_n_tiles;
   int spin;  // 1: TMA / MMA threads poll their ring barriers (see tc_gemm.cu)
-  int tma_store;  // 1: fp32 result tiles leave through TMA bulk stores (same epilogue as tc_gemm.cu)
+  int tma_store;  // 1: result tiles leave through TMA bulk stores (same epilogue as tc_gemm.cu)
   // QKV mode (qS > 0, TMA-store epilogue only): the [M, 3*H*64] result goes straight into the attention layout through
-  // tmQ / tmK (3-D {64, S_pad, B*H}) and tmV (2-D {S_pad, B*H*64}, transposed chunks); see the epilogue
+  // tmQ / tmK (3-D {64, S_pad, B*H}); V^T chunks are written from registers; see the epilogue
   int qS, qH, qB, qSpad;
-  float* qkv_q; float* qkv_k; float* qkv_vt;
+  void* qkv_q; void* qkv_k; void* qkv_vt;
   unsigned long long* trace;  // debug timeline of cluster 0's leader CTA (same layout as gemm_stamp in tc_gemm.cu)
 };
 
@@ -107,7 +110,8 @@ constexpr size_t g2_smem_bytes() {
   return (size_t)g2_stages<BN>() * (BM * 128 + (BN / 2) * 128) + EPI_WARPS * 32 * EPI_LD * 4 + 1024 + 256;
 }
 
-template <bool TF32, int BN>
+// H16: the TMA-store epilogue writes 16-bit results (compile-time so that the fp32 epilogue keeps its register budget)
+template <bool TF32, int BN, bool H16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmQ,
@@ -168,7 +172,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc<TF32>(2 * BM, BN);
+      const uint32_t idesc = TF32 ? make_idesc<true>(2 * BM, BN) : make_idesc_h16(e.op_f16 != 0, 2 * BM, BN);
       uint32_t it = 0, tile_iter = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
         const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
@@ -249,6 +253,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
             if (etr) g2_stamp(e, tile_iter, 9);
           }
+          // 16-bit results (H16): the group's chunks are packed and staged one after the other and leave together as one
+          // {64 x 32} box (128-byte rows); a lone chunk leaves as a {32 x 32} box (tc_epilogue.cuh)
+          const int n_grp0 = n0 + c0 * 32;
+          int nvalid = 0;
+#pragma unroll
+          for (int cc = 0; cc < GRP; ++cc)
+            if (c0 + cc < NCH && n_grp0 + cc * 32 < e.N) nvalid = cc + 1;
+          // fused QKV scatter: groups start at multiples of 64 columns, so a group is the 64 head-dim values of ONE head of
+          // Q, K or V.  V^T groups are written straight from registers.
+          const bool vt_grp = H16 && e.qS > 0 && n_grp0 >= 2 * e.qH * 64;
+          if (H16 && !vt_grp && nvalid > 0) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
 #pragma unroll
           for (int cc = 0; cc < GRP; ++cc) {
             const int ncol = n0 + (c0 + cc) * 32;
@@ -274,7 +292,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
                 o[4 * i + 2] += res[cc][i].z; o[4 * i + 3] += res[cc][i].w;
               }
             }
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if constexpr (H16) {
+              const bool f16 = e.c_h16 == 2;
+              if (vt_grp) {
+                // for a fixed head-dim index the 32 lanes write 32 consecutive tokens: one coalesced 64-byte store
+                const int hh = (ncol - 2 * e.qH * 64) >> 6, d0 = ncol & 63;
+                const long long m = (long long)m0 + q * 32 + lane;
+                if (m < e.M) {
+                  const int b2 = (int)(m / e.qS), s2 = (int)(m - (long long)b2 * e.qS);
+                  uint16_t* dst = reinterpret_cast<uint16_t*>(e.qkv_vt) + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
+#pragma unroll
+                  for (int d = 0; d < 32; ++d) dst[(long long)d * e.qSpad] = cvt_h16_rt(o[d], f16);
+                }
+                continue;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t u0 = pack_h16_rt(o[8 * j + 0], o[8 * j + 1], f16), u1 = pack_h16_rt(o[8 * j + 2], o[8 * j + 3], f16);
+                const uint32_t u2 = pack_h16_rt(o[8 * j + 4], o[8 * j + 5], f16), u3 = pack_h16_rt(o[8 * j + 6], o[8 * j + 7], f16);
+                uint32_t addr;
+                if (nvalid == 2) addr = st_row + (uint32_t)(((cc * 4 + j) ^ (lane & 7)) * 16);
+                else { const uint32_t lin = (uint32_t)(lane * 64 + j * 16); addr = st_base + (lin ^ (((lin >> 7) & 7u) << 4)); }
+                sts128_u32(addr, u0, u1, u2, u3);
+              }
+              continue;
+            } else {
+            if (lane == 0) tma_store_wait_read();
             __syncwarp();
             if (e.qS > 0) {
               // ---- fused QKV scatter.  A chunk is 32 tokens x 32 columns of one head (32 | 64): Q / K chunks are stored as
@@ -293,12 +336,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
                 if (m < e.M) {
                   const int b2 = (int)(m / e.qS), s2 = (int)(m - (long long)b2 * e.qS);
                   if (which < 2) {
-                    float* dst = (which == 0 ? e.qkv_q : e.qkv_k) + (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64 + d0;
+                    float* dst = reinterpret_cast<float*>(which == 0 ? e.qkv_q : e.qkv_k) + (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64 + d0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                       *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                   } else {
-                    float* dst = e.qkv_vt + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
+                    float* dst = reinterpret_cast<float*>(e.qkv_vt) + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
 #pragma unroll
                     for (int d = 0; d < 32; ++d) dst[(long long)d * e.qSpad] = o[d];
                   }
@@ -310,13 +353,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
                 sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
               fence_proxy_async();
               __syncwarp();
-              if (lane == 0) {
-                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                                 reinterpret_cast<uint64_t>(which == 0 ? &tmQ : &tmK)),
-                             "r"(st_base), "r"(d0), "r"(ss0), "r"(bb * e.qH + hh)
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
+              if (lane == 0) tma_store_3d(which == 0 ? &tmQ : &tmK, st_base, d0, ss0, bb * e.qH + hh);
               continue;
             }
 #pragma unroll
@@ -324,19 +361,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
               sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tmC)),
-                           "r"(st_base), "r"(ncol), "r"(m0 + q * 32)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (lane == 0) tma_store_2d(&tmC, st_base, ncol, m0 + q * 32);
+            }  // !H16
+          }
+          if (H16 && !vt_grp && nvalid > 0) {
+            if (e.qS > 0) {
+              // Q / K group: one {64, 32, 1} box, or row by row where the 32 tokens straddle a batch boundary (a TMA box
+              // cannot be clipped at S < S_pad, and the padding rows must stay zero)
+              const int D = e.qH * 64;
+              const int which = n_grp0 / D, hh = (n_grp0 - which * D) >> 6;
+              const int mb = m0 + q * 32;
+              const int bb = mb / e.qS, ss0 = mb - bb * e.qS;
+              if (ss0 + 32 > e.qS || bb >= e.qB) {  // warp-uniform
+                __syncwarp();
+                const long long m = (long long)mb + lane;
+                if (m < e.M) {
+                  const int b2 = (int)(m / e.qS), s2 = (int)(m - (long long)b2 * e.qS);
+                  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(which == 0 ? e.qkv_q : e.qkv_k) +
+                                                        (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64);
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {  // this lane's own staged row
+                    const float4 v = lds128(st_row + (uint32_t)((u ^ (lane & 7)) * 16));
+                    dst[u] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                  }
+                }
+                __syncwarp();
+              } else {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tma_store_3d(which == 0 ? &tmQ : &tmK, st_base, 0, ss0, bb * e.qH + hh);
+              }
+            } else {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) tma_store_2d(nvalid == 2 ? &tmC : &tmQ /* {32 x 32} box */, st_base, n_grp0, m0 + q * 32);
             }
           }
           if (e.residual && c0 + GRP < NCH) load_res(c0 + GRP);
         }
         if (etr) g2_stamp(e, tile_iter, 10);
       }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (lane == 0) tma_store_wait_all();
       __syncwarp();
     } else {
     const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
@@ -411,12 +476,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
           }
           if (vec_ok) {
             if (e.residual) { o[0] += res[i].x; o[1] += res[i].y; o[2] += res[i].z; o[3] += res[i].w; }
-            if (e.c_bf16) {
-              __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+            if (e.c_h16) {
               uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + m * e.ldc + n) = pk;
+              pk.x = pack_h16_rt(o[0], o[1], e.c_h16 == 2);
+              pk.y = pack_h16_rt(o[2], o[3], e.c_h16 == 2);
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.C) + m * e.ldc + n) = pk;
             } else {
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -425,7 +489,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
               if (n + j >= e.N) break;
               float x = o[j];
               if (e.residual) x += e.residual[m * e.ldr + n + j];
-              if (e.c_bf16) reinterpret_cast<__nv_bfloat16*>(e.C)[m * e.ldc + n + j] = __float2bfloat16_rn(x);
+              if (e.c_h16) reinterpret_cast<uint16_t*>(e.C)[m * e.ldc + n + j] = cvt_h16_rt(x, e.c_h16 == 2);
               else reinterpret_cast<float*>(e.C)[m * e.ldc + n + j] = x;
             }
           }
@@ -446,15 +510,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 
 struct QkvMaps { CUtensorMap q, k, v; };
 
-template <bool TF32, int BN>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStream_t st, const QkvMaps* qm = nullptr) {
+template <bool TF32, int BN, bool H16>
+int launch2k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmQ,
+             const CUtensorMap& tmK, const Epi2Args& e, int clusters, const char* what, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = g2_smem_bytes<BN>();
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tc2_kernel<TF32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tc2_kernel<TF32, BN, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(err));
     attr_set = true;
   }
+  gemm_tc2_kernel<TF32, BN, H16><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, tmQ, tmK, tmA, e);
+  return check_launch(what);
+}
+
+template <bool TF32, int BN>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStream_t st, const QkvMaps* qm = nullptr) {
   e.num_m_tiles = (int)ceil_div<long long>(e.M, 2 * BM);
   e.num_n_tiles = ceil_div(e.N, BN);
   int dev = 0, sms = 148;
@@ -462,26 +533,41 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStre
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
-  CUtensorMap tmC = tmA;  // placeholder when unused
+  CUtensorMap tmC = tmA, tmC1 = tmA;  // placeholders when unused
   e.tma_store = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const char* ts = getenv("MMVID_GEMM_TMA_STORE");
-  if (qm == nullptr && !(ts && ts[0] == '0') && !e.c_bf16 && e.N % 32 == 0 && e.ldc % 4 == 0 && al16(e.C) &&
+  const int csz = e.c_h16 ? 2 : 4;
+  if (qm == nullptr && !(ts && ts[0] == '0') && !(TF32 && e.c_h16) && e.N % 32 == 0 && (e.ldc * csz) % 16 == 0 && al16(e.C) &&
       (!e.residual || (e.ldr % 4 == 0 && al16(e.residual))) && (!e.bias || al16(e.bias))) {
     uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
-    uint64_t str[1] = {(uint64_t)e.ldc * 4};
-    uint32_t box[2] = {32, 32};
-    int rc = make_tensor_map(&tmC, e.C, DT_F32_EXACT, 2, dims, str, box);
-    if (rc) return rc;
+    uint64_t str[1] = {(uint64_t)e.ldc * csz};
+    if (e.c_h16) {
+      // 16-bit results: {64 x 32} boxes (two accumulator chunks, 128-byte rows) + {32 x 32} boxes for a lone chunk
+      const int dt = e.c_h16 == 2 ? MMVID_DT_F16 : MMVID_DT_BF16;
+      uint32_t box[2] = {64, 32}, box1[2] = {32, 32};
+      int rc = make_tensor_map(&tmC, e.C, dt, 2, dims, str, box);
+      if (rc) return rc;
+      rc = make_tensor_map(&tmC1, e.C, dt, 2, dims, str, box1);
+      if (rc) return rc;
+    } else {
+      uint32_t box[2] = {32, 32};
+      int rc = make_tensor_map(&tmC, e.C, DT_F32_EXACT, 2, dims, str, box);
+      if (rc) return rc;
+    }
     e.tma_store = 1;
   }
   if (qm != nullptr) {
     e.tma_store = 1;  // the QKV scatter only exists in the TMA-store epilogue (the caller checked its preconditions)
-    gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmA, qm->q, qm->k, qm->v, e);
-    return check_launch("gemm_tc2_qkv");
+    if constexpr (!TF32) {
+      if (e.c_h16) return launch2k<TF32, BN, true>(tmA, tmB, tmA, qm->q, qm->k, e, clusters, "gemm_tc2_qkv", st);
+    }
+    return launch2k<TF32, BN, false>(tmA, tmB, tmA, qm->q, qm->k, e, clusters, "gemm_tc2_qkv", st);
   }
-  gemm_tc2_kernel<TF32, BN><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, tmA, tmA, tmA, e);
-  return check_launch("gemm_tc2");
+  if constexpr (!TF32) {
+    if (e.c_h16 && e.tma_store) return launch2k<TF32, BN, true>(tmA, tmB, tmC, tmC1, tmA, e, clusters, "gemm_tc2", st);
+  }
+  return launch2k<TF32, BN, false>(tmA, tmB, tmC, tmC1, tmA, e, clusters, "gemm_tc2", st);
 }
 
 }  // namespace
@@ -509,7 +595,9 @@ extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const
     if (rc) return rc;
   }
   Epi2Args e{};
-  e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc; e.c_bf16 = c_dtype == MMVID_DT_BF16;
+  e.bias = bias; e.residual = residual; e.ldr = ldr; e.C = C; e.ldc = ldc;
+  e.c_h16 = c_dtype == MMVID_DT_BF16 ? 1 : (c_dtype == MMVID_DT_F16 ? 2 : 0);
+  e.op_f16 = precision == MMVID_F16;
   e.M = M; e.N = N; e.K = K; e.act = act;
   { const char* v = getenv("MMVID_GEMM_SPIN"); e.spin = v ? atoi(v) : 0; }
   e.trace = mmvid::g_gemm_trace;
@@ -518,53 +606,54 @@ extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const
   return tf32 ? launch2<true, 128>(tmA, tmB, e, st) : launch2<false, 128>(tmA, tmB, e, st);
 }
 
-// Fused QKV projection on the CTA-pair kernel (tf32, fp32 Q / K / V^T): qkv = A W^T + b scattered straight into
-// Q, K [B,H,S_pad,64] and V^T [B,H,64,S_pad] by TMA stores.  Returns MMVID_EINVAL-free "not applicable" (1) when the
-// preconditions do not hold, so that mmvid_linear_qkv can fall back to the single-CTA kernel.
+// Fused QKV projection on the CTA-pair kernel: qkv = A W^T + b scattered straight into Q, K [B,H,S_pad,64] (TMA stores) and
+// V^T [B,H,64,S_pad] (coalesced register stores).  tf32: fp32 operands and fp32 Q / K / V^T; 16-bit kinds: operands and
+// outputs in the precision's 16-bit type.  Returns 1 ("not applicable") when the preconditions do not hold, so that
+// mmvid_linear_qkv can fall back to the single-CTA kernel.
 extern "C" int mmvid_linear_qkv_tc2(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* q,
-                                    void* k, void* vt, int B, int H, int S, int S_pad, cudaStream_t st) {
+                                    void* k, void* vt, int B, int H, int S, int S_pad, int precision, cudaStream_t st) {
   const long long M = (long long)B * S;
   const int N = 3 * H * 64, K = H * 64;
+  const bool tf32 = precision == MMVID_TF32;
+  const int esz = tf32 ? 4 : 2, BKE = tf32 ? 32 : 64;
+  const int dt_op = tf32 ? MMVID_DT_F32 : (precision == MMVID_F16 ? MMVID_DT_F16 : MMVID_DT_BF16);
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (S < 32 || N % 256 != 0 || M < 1024 || !al16(q) || !al16(k) || !al16(vt) || (bias && !al16(bias)) || S_pad % 4 != 0) return 1;
+  if (S < 32 || N % 256 != 0 || M < 1024 || !al16(q) || !al16(k) || !al16(vt) || (bias && !al16(bias)) || S_pad % 8 != 0) return 1;
   CUtensorMap tmA, tmB;
   QkvMaps qm;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    uint64_t str[1] = {(uint64_t)lda * 4};
-    uint32_t box[2] = {32, (uint32_t)BM};
-    int rc = make_tensor_map(&tmA, A, MMVID_DT_F32, 2, dims, str, box);
+    uint64_t str[1] = {(uint64_t)lda * esz};
+    uint32_t box[2] = {(uint32_t)BKE, (uint32_t)BM};
+    int rc = make_tensor_map(&tmA, A, dt_op, 2, dims, str, box);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
-    uint64_t str[1] = {(uint64_t)ldw * 4};
-    uint32_t box[2] = {32, 128};
-    int rc = make_tensor_map(&tmB, W, MMVID_DT_F32, 2, dims, str, box);
+    uint64_t str[1] = {(uint64_t)ldw * esz};
+    uint32_t box[2] = {(uint32_t)BKE, 128};
+    int rc = make_tensor_map(&tmB, W, dt_op, 2, dims, str, box);
     if (rc) return rc;
   }
   {
+    // Q / K boxes: tf32 one 32-column chunk of 32 tokens, 16-bit a whole head (two chunks) of 32 tokens
     uint64_t dims[3] = {64, (uint64_t)S_pad, (uint64_t)B * H};
-    uint64_t str[2] = {64 * 4, (uint64_t)S_pad * 64 * 4};
-    uint32_t box[3] = {32, 32, 1};
-    int rc = make_tensor_map(&qm.q, q, DT_F32_EXACT, 3, dims, str, box);
+    uint64_t str[2] = {(uint64_t)64 * esz, (uint64_t)S_pad * 64 * esz};
+    uint32_t box[3] = {tf32 ? 32u : 64u, 32, 1};
+    int rc = make_tensor_map(&qm.q, q, tf32 ? DT_F32_EXACT : dt_op, 3, dims, str, box);
     if (rc) return rc;
-    rc = make_tensor_map(&qm.k, k, DT_F32_EXACT, 3, dims, str, box);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[2] = {(uint64_t)S_pad, (uint64_t)B * H * 64};
-    uint64_t str[1] = {(uint64_t)S_pad * 4};
-    uint32_t box[2] = {32, 32};
-    int rc = make_tensor_map(&qm.v, vt, DT_F32_EXACT, 2, dims, str, box);
+    rc = make_tensor_map(&qm.k, k, tf32 ? DT_F32_EXACT : dt_op, 3, dims, str, box);
     if (rc) return rc;
   }
+  qm.v = qm.q;  // unused: V^T chunks are written from registers
   Epi2Args e{};
-  e.bias = bias; e.residual = nullptr; e.ldr = 0; e.C = nullptr; e.ldc = 0; e.c_bf16 = 0;
+  e.bias = bias; e.residual = nullptr; e.ldr = 0; e.C = nullptr; e.ldc = 0;
+  e.c_h16 = tf32 ? 0 : (precision == MMVID_F16 ? 2 : 1);
+  e.op_f16 = precision == MMVID_F16;
   e.M = M; e.N = N; e.K = K; e.act = MMVID_ACT_NONE;
   e.qS = S; e.qH = H; e.qB = B; e.qSpad = S_pad;
-  e.qkv_q = static_cast<float*>(q); e.qkv_k = static_cast<float*>(k); e.qkv_vt = static_cast<float*>(vt);
+  e.qkv_q = q; e.qkv_k = k; e.qkv_vt = vt;
   { const char* v = getenv("MMVID_GEMM_SPIN"); e.spin = v ? atoi(v) : 0; }
   e.trace = mmvid::g_gemm_trace;
-  return launch2<true, 256>(tmA, tmB, e, st, &qm);
+  return tf32 ? launch2<true, 256>(tmA, tmB, e, st, &qm) : launch2<false, 256>(tmA, tmB, e, st, &qm);
 }

@@ -203,7 +203,7 @@ class DALLE(nn.Module):
         if rows.shape[0] <= 16:
             h = ops.layernorm(rows, ln.weight, ln.bias, 1e-5)
             return ops.linear_small_m(h, lin.weight.detach()[col_lo:col_hi], lin.bias.detach()[col_lo:col_hi])
-        h = ops.layernorm(rows, ln.weight, ln.bias, 1e-5, out_dtype=torch.bfloat16 if prec == 2 else torch.float32)
+        h = ops.layernorm(rows, ln.weight, ln.bias, 1e-5, out_dtype=ops.act_dtype(prec))
         w = self.transformer._w(lin.weight, prec)[col_lo:col_hi]
         return ops.linear(h, w, lin.bias.detach()[col_lo:col_hi], precision=prec)
 
@@ -247,6 +247,11 @@ class DALLE(nn.Module):
         return logits
 
     # ------------------------------------------------------------------------------------------ sampling
+    def generate_tokens(self, text, visual=None, max_new=None, **kwargs):
+        """The sampling loop of generate_images alone: long [B, max_new] image-token ids (no VQGAN decode)."""
+        return self.generate_images(text, visual=visual, max_new=max_new if max_new is not None else self.target_seq_len,
+                                    **kwargs)[2]
+
     @torch.no_grad()
     @eval_decorator
     def generate_images(self, text, *, clip=None, visual=None, mask=None, filter_thres=0.5, temperature=1.0,
@@ -300,7 +305,9 @@ class DALLE(nn.Module):
             head_b = lin.bias.detach()[lo:lo + self.num_image_tokens]
             logits_buf = torch.empty(B, self.num_image_tokens, device=dev, dtype=torch.float32)
         trace = kwargs.get("logits_trace")  # optional list: receives the [B, 1024] image logits of every step (tests)
-        for t in range(self.target_seq_len):
+        max_new = kwargs.get("max_new")     # stop after this many sampled tokens and return them (parity tests)
+        n_steps = self.target_seq_len if max_new is None else min(int(max_new), self.target_seq_len)
+        for t in range(n_steps):
             if trace is not None:
                 trace.append(logits.clone())
             # top_k keeps >= 1024 entries (k = 25888 at the default 0.5), so only the masked logits (-FLT_MAX -> prob 0)
@@ -313,7 +320,7 @@ class DALLE(nn.Module):
             else:
                 sample = torch.multinomial(probs_img, 1)
             out_tokens[:, t] = sample[:, 0]
-            if t == self.target_seq_len - 1:
+            if t == n_steps - 1:
                 break
             # ---- one decode step at sequence position P + t
             ops.embed_gather(xt, [dict(ids=sample, seq_off=0, table=self.image_emb.weight.detach(),
@@ -351,6 +358,8 @@ class DALLE(nn.Module):
                 a = ops.linear_small_m(a, blk.mlp.c_fc.weight.detach(), blk.mlp.c_fc.bias, act=1)
                 h = ops.linear_small_m(a, blk.mlp.c_proj.weight.detach(), blk.mlp.c_proj.bias, residual=h)
             logits = self._head_rows(h, lo, lo + self.num_image_tokens)
+        if max_new is not None:
+            return None, [], out_tokens[:, :n_steps]
         img_seq = out_tokens.reshape(-1, self.image_seq_len) if self.num_targets > 1 else out_tokens
         images = self.vae.decode(img_seq)
         if self.num_targets > 1:

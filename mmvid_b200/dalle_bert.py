@@ -273,8 +273,7 @@ class BERT(nn.Module):
     def _head(self, rows, seq):
         """nn.Sequential(LayerNorm, Linear) on [M, D] rows (dalle_bert.py:414-425)."""
         prec = PRECISIONS[self.precision]
-        h = ops.layernorm(rows, seq[0].weight, seq[0].bias, 1e-5,
-                          out_dtype=torch.bfloat16 if prec == 2 else torch.float32)
+        h = ops.layernorm(rows, seq[0].weight, seq[0].bias, 1e-5, out_dtype=ops.act_dtype(prec))
         w = self.transformer._w(seq[1].weight, prec)
         return ops.linear(h, w, seq[1].bias, precision=prec)
 
@@ -386,11 +385,11 @@ class BERT(nn.Module):
 
     def _transformer_train(self, tokens):
         from .autograd import AttentionFn, LayerNormFn, LinearFn
-        from ._lib import ACT_NONE, ACT_QUICKGELU, BF16
+        from ._lib import ACT_NONE, ACT_QUICKGELU, H16
         tr = self.transformer
         prec = PRECISIONS[tr.precision]
-        if prec == BF16:
-            prec = 1  # training runs the tf32 tensor-core path (bf16 activations are an inference-only mode)
+        if prec in H16:
+            prec = 1  # training runs the tf32 tensor-core path (16-bit activations are an inference-only mode)
         B, S, D = tokens.shape
         H = tr.transformer.heads
         x = tokens.reshape(B * S, D)
@@ -409,8 +408,8 @@ class BERT(nn.Module):
         from ._lib import ACT_NONE, FP32
         h = LayerNormFn.apply(rows, seq[0].weight, seq[0].bias, 1e-5)
         prec = PRECISIONS[self.transformer.precision]
-        if prec == 2:
-            prec = 1                      # bf16 is inference-only; training GEMMs run tf32
+        if prec in (2, 3):
+            prec = 1                      # bf16 / fp16 are inference-only; training GEMMs run tf32
         if seq[1].weight.shape[0] < 8:
             prec = FP32                   # scalar REL / VID heads: CUDA-core path
         return LinearFn.apply(h, seq[1].weight, seq[1].bias, ACT_NONE, prec)

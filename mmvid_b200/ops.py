@@ -8,7 +8,8 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from ._lib import ACT_NONE, ACT_QUICKGELU, ACT_SWISH, BF16, DT_BF16, DT_F32, FP32, MASK_CAUSAL, MASK_NONE, MASK_PREV, TF32  # noqa: F401
+from ._lib import (ACT_NONE, ACT_QUICKGELU, ACT_SWISH, BF16, DT_BF16, DT_F16, DT_F32, F16, FP32, H16, MASK_CAUSAL,  # noqa: F401
+                   MASK_NONE, MASK_PREV, TF32)
 
 
 def _stream():
@@ -32,7 +33,15 @@ def _dt(t):
         return DT_F32
     if t.dtype == torch.bfloat16:
         return DT_BF16
+    if t.dtype == torch.float16:
+        return DT_F16
     raise RuntimeError(f"unsupported dtype {t.dtype}")
+
+
+def act_dtype(precision):
+    """torch dtype of GEMM operands / inter-kernel activations for a precision (fp32 for FP32 and TF32)."""
+    precision = precision_id(precision)
+    return torch.bfloat16 if precision == BF16 else (torch.float16 if precision == F16 else torch.float32)
 
 
 def precision_id(p):
@@ -208,7 +217,7 @@ def attention_tc(qkv, B, S, H, mask_kind, prev_rows_host, precision, out_dtype=t
     lib = L.load()
     precision = precision_id(precision)
     S_pad = (S + 127) // 128 * 128
-    dt = torch.float32 if precision == TF32 else torch.bfloat16
+    dt = act_dtype(precision)
     dev = qkv.device
     q = torch.empty(B, H, S_pad, 64, device=dev, dtype=dt)
     k = torch.empty(B, H, S_pad, 64, device=dev, dtype=dt)
@@ -225,7 +234,7 @@ def alloc_qkv_buffers(B, H, S, precision, device):
     """Zero-initialised Q,K [B,H,S_pad,64] and V^T [B,H,64,S_pad] (padding must stay zero: P x garbage = NaN)."""
     precision = precision_id(precision)
     S_pad = (S + 127) // 128 * 128
-    dt = torch.float32 if precision == TF32 else torch.bfloat16
+    dt = act_dtype(precision)
     q = torch.zeros(B, H, S_pad, 64, device=device, dtype=dt)
     k = torch.zeros(B, H, S_pad, 64, device=device, dtype=dt)
     vt = torch.zeros(B, H, 64, S_pad, device=device, dtype=dt)

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
-from ._lib import ACT_QUICKGELU, BF16, FP32, MASK_CAUSAL, MASK_NONE, MASK_PREV, TF32, PRECISIONS
+from ._lib import ACT_QUICKGELU, BF16, FP32, H16, MASK_CAUSAL, MASK_NONE, MASK_PREV, TF32, PRECISIONS  # noqa: F401
 
 
 class ResidualAttentionBlock(nn.Module):
@@ -39,18 +39,23 @@ class Transformer(nn.Module):
         self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
 
 
-class _Bf16Cache:
-    """bf16 copies of fp32 parameters for the kind::f16 GEMMs, refreshed when a parameter is modified."""
+class _H16Cache:
+    """bf16 / fp16 copies of fp32 parameters for the kind::f16 GEMMs, refreshed when a parameter is modified.
+    (CLIP's Linear weights went through fp16 in the reference's own loader - clip_model.py:435-458 - so the fp16 copies
+    of a CLIP-initialised transformer are exact.)"""
 
     def __init__(self):
         self._d = {}
 
-    def get(self, p):
-        key = id(p)
+    def get(self, p, dtype=torch.bfloat16):
+        key = (id(p), dtype)
         tag = (p.data_ptr(), p._version, _lib.weights_epoch())
         hit = self._d.get(key)
         if hit is None or hit[0] != tag:
-            hit = (tag, p.detach().to(torch.bfloat16).contiguous())
+            w = p.detach()
+            if dtype == torch.float16:
+                w = w.clamp(-65504.0, 65504.0)
+            hit = (tag, w.to(dtype).contiguous())
             self._d[key] = hit
         return hit[1]
 
@@ -99,7 +104,7 @@ class OpenAICLIPTransformer(nn.Module):
         else:
             self.mask_kind, self.mask_rows = MASK_NONE, ()
         self.precision = precision
-        self._bf16 = _Bf16Cache()
+        self._bf16 = _H16Cache()
         self._rows_dev = None
 
     # ------------------------------------------------------------------------------------------
@@ -116,7 +121,7 @@ class OpenAICLIPTransformer(nn.Module):
         return self._qkv_bufs
 
     def _w(self, p, prec):
-        return self._bf16.get(p) if prec == BF16 else p.detach()
+        return self._bf16.get(p, ops.act_dtype(prec)) if prec in H16 else p.detach()
 
     @torch.no_grad()
     def forward(self, x, collect=None, kv_out=None, **kwargs):
@@ -126,7 +131,7 @@ class OpenAICLIPTransformer(nn.Module):
         H = self.transformer.heads
         assert D == self.transformer.width
         x = x.contiguous().float().view(B * S, D)
-        act_dt = torch.bfloat16 if prec == BF16 else torch.float32
+        act_dt = ops.act_dtype(prec)
         first = True
         for li, blk in enumerate(self.transformer.resblocks):
             h = ops.layernorm(x, blk.ln_1.weight, blk.ln_1.bias, 1e-5, out_dtype=act_dt)

@@ -296,6 +296,37 @@ def bert_control_emb(spec, sd, text, visual_tokens=None):
     return torch.cat((control, after_emb), dim=1)
 
 
+def erase_codebook_face(spec, visual_tokens, vc_mode, face_mode):
+    """BERT.erase_codebook_face (dalle_bert.py:796-848) for the deterministic branches (face_mode given, or a vc_mode
+    that never draws): visual-control token grids [B, V*n] with everything outside a window set to [MASK].
+    The windows are hard-coded for 8 x 8 grids in the reference; they are applied as written whatever the fmap."""
+    f = spec.fmap
+    img = visual_tokens.view(visual_tokens.shape[0], -1, f, f)
+    if vc_mode == "shape_4x4":
+        out = img.clone()
+        out[:, :, 1:3, 1:3] = spec.MASK  # :841
+        return out.view_as(visual_tokens)
+    out = torch.full_like(img, spec.MASK)
+    if vc_mode == "face_8x8":
+        assert face_mode is not None, "face_mode=None draws from random.random() (:806)"
+        if face_mode == "eyes_nose":
+            out[:, :, 2:5, 1:7] = img[:, :, 2:5, 1:7]   # :808
+        else:
+            out[:, :, 5:7, 2:6] = img[:, :, 5:7, 2:6]   # :810
+    elif vc_mode == "face2_8x8":
+        out[:, 0] = img[:, 0]                           # :815
+        out[:, 1:, 2:6, 2:6] = img[:, 1:, 2:6, 2:6]     # :816
+    elif vc_mode == "face3_8x8":
+        out[:, 0] = img[:, 0]                           # :821
+        out[:, :, 2:6, 2:6] = img[:, :, 2:6, 2:6]       # :822
+    elif vc_mode in ("mask_8x8", "mask2_8x8"):
+        assert face_mode is not None, "face_mode=None draws from np.random.choice (:826)"
+        out[:, :, 1:7, 1:7] = img[:, :, 1:7, 1:7]       # strategy 3 (:829, :837-839)
+    else:
+        raise NotImplementedError(vc_mode)
+    return out.view_as(visual_tokens)
+
+
 def _to_logits(x, sd, p):
     """nn.Sequential(LayerNorm(dim), Linear) (dalle_bert.py:414-425)."""
     h = F.layer_norm(x, (x.shape[-1],), sd[p + "0.weight"], sd[p + "0.bias"], 1e-5)

@@ -24,6 +24,10 @@ BERT_CASES = {
                         image_size=128, cvae=False, seed=21, batch=1),
     "bert_shapeA": dict(dim=768, layers=12, text_seq_len=64, vocab=49408, num_visuals=0, num_targets=8,
                         image_size=256, cvae=False, seed=22, batch=1),
+    # BASELINE config 4 (text + mask conditioning, scripts/mmvoxceleb/text_and_mask): one cVAE-encoded visual-control frame
+    # whose token grid is windowed by vc_mode='mask_8x8' (face_mode given => deterministic strategy 3), S = 629
+    "bert_shapeB_vis": dict(dim=768, layers=12, text_seq_len=50, vocab=49408, num_visuals=1, num_targets=8,
+                            image_size=128, cvae=True, seed=23, batch=2, vc_mode="mask_8x8", face_mode="mouth"),
 }
 
 ARTV_CASES = {

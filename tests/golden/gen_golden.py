@@ -123,11 +123,18 @@ def gen_bert(name, cfg):
         visual = synth.synth_frames(B, cfg["num_visuals"], cfg["image_size"], cfg["seed"] + 5)
     out = dict(cfg=cfg)
     t0 = time.time()
-    control_ref = model(text, visual=visual, return_loss=False)
+    vc = dict(vc_mode=cfg["vc_mode"], face_mode=cfg.get("face_mode")) if cfg.get("vc_mode") else {}
+    control_ref = model(text, visual=visual, return_loss=False, **vc)
     vis_tok = None
     if visual is not None:
         p = "cvae." if cfg["cvae"] else "vae."
         vis_tok = O.vae_get_codebook_indices(visual.reshape(-1, *visual.shape[2:]), O.sub_state_dict(sd, p)).view(B, -1)
+        if vc:
+            # the reference's own tokens after its own erase hook, to pin the oracle's restatement of it
+            ref_tok = model.erase_codebook_face(model.get_image_tokens(visual, which_vae="cvae"), **vc)
+            out["visual_tokens_raw"] = vis_tok.clone()
+            vis_tok = O.erase_codebook_face(spec, vis_tok, **vc)
+            assert torch.equal(vis_tok, ref_tok), (name, "erase_codebook_face")
         out["visual_tokens"] = vis_tok.clone()
     control_or = O.bert_control_emb(spec, sd, text, vis_tok)
     e = relerr(control_or, control_ref)

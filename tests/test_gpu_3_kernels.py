@@ -1,7 +1,8 @@
 """GPU parity of each C-ABI kernel against a plain PyTorch fp32 statement of the same op (run with -m gpu).
 
 Tolerances: fp32 CUDA-core path ~1e-5 norm-relative (summation order only); TF32 tensor-core path 1e-3
-(north_star's bar); BF16 path 2e-2 (reported, throughput mode).  Integer outputs must be bit-exact."""
+(north_star's bar); FP16 path (kind::f16 with fp16 operands: the tf32 mantissa) 1e-3 as well; BF16 path 2e-2 (reported,
+wide-range 16-bit mode).  Integer outputs must be bit-exact."""
 import math
 
 import pytest
@@ -12,7 +13,13 @@ from helpers import relerr
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 2e-2}
+TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 2e-2, "fp16": 1e-3}
+H16 = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def _op(t, prec):
+    """operand in the precision's own dtype (16-bit kinds take 16-bit operands)"""
+    return t.to(H16[prec]) if prec in H16 else t
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -73,7 +80,7 @@ def test_layernorm(rows, D):
     assert relerr(ops.layernorm(x, w, b, out_dtype=torch.bfloat16).float(), ref) < 5e-3
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("M,N,K", [(1, 64, 64), (130, 192, 128), (2115, 2304, 768), (565, 768, 3072), (300, 1024, 768)])
 def test_linear_bias_act_residual(prec, M, N, K):
     ops = _ops()
@@ -84,19 +91,13 @@ def test_linear_bias_act_residual(prec, M, N, K):
     res = torch.randn(M, N, generator=g).cuda()
     ref0 = F.linear(a.double(), w.double(), bias.double())
     ref = (ref0 * torch.sigmoid(1.702 * ref0) + res.double()).float()
-    if prec == "bf16":
-        out = ops.linear(a.bfloat16(), w.bfloat16(), bias, act=ops.ACT_QUICKGELU, residual=res, precision=prec)
-    else:
-        out = ops.linear(a, w, bias, act=ops.ACT_QUICKGELU, residual=res, precision=prec)
+    out = ops.linear(_op(a, prec), _op(w, prec), bias, act=ops.ACT_QUICKGELU, residual=res, precision=prec)
     e = relerr(out, ref)
     assert e < TOL[prec], f"{prec} {M}x{N}x{K}: {e}"
     # plain (no epilogue) + in-place residual aliasing
     ref2 = (F.linear(a.double(), w.double()) + res.double()).float()
     buf = res.clone()
-    if prec == "bf16":
-        ops.linear(a.bfloat16(), w.bfloat16(), None, residual=buf, precision=prec, out=buf)
-    else:
-        ops.linear(a, w, None, residual=buf, precision=prec, out=buf)
+    ops.linear(_op(a, prec), _op(w, prec), None, residual=buf, precision=prec, out=buf)
     assert relerr(buf, ref2) < TOL[prec]
 
 
@@ -110,6 +111,32 @@ def test_linear_bf16_output_and_unaligned_n():
     assert relerr(out, ref) < 1e-3
     o16 = ops.linear(a.bfloat16(), w[:128].bfloat16().contiguous(), precision="bf16", out_dtype=torch.bfloat16)
     assert o16.dtype == torch.bfloat16 and relerr(o16.float(), ref[:, :128]) < 2e-2
+    h16 = ops.linear(a.half(), w[:128].half().contiguous(), precision="fp16", out_dtype=torch.float16)
+    assert h16.dtype == torch.float16 and relerr(h16.float(), ref[:, :128]) < 1e-3
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,N,K,act", [(1400, 3072, 768, 1), (1300, 768, 768, 0), (1100, 1024, 768, 0), (1500, 2368, 768, 1),
+                                       (300, 96, 256, 0), (700, 160, 128, 1)])
+def test_16bit_results_through_tma_stores(prec, M, N, K, act):
+    """16-bit outputs of every tile flavour (CTA-pair 256 / 192 / 128 wide, single-CTA 128 / 64 wide): 64-column groups
+    leave as one {64 x 32} box, lone 32-column chunks (N = 2368 = 37 x 64, N = 96, N = 160) as {32 x 32} boxes; the M
+    tail is clipped by the TMA unit.  fp16 stores saturate instead of producing inf."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = F.linear(a.double(), w.double(), bias.double())
+    if act:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    out = ops.linear(_op(a, prec), _op(w, prec), bias, act=act, precision=prec, out_dtype=H16[prec])
+    assert out.dtype == H16[prec]
+    # the 16-bit store rounds once more: half an ulp of an 11-bit (fp16) / 8-bit (bf16) significand
+    assert relerr(out.float(), ref.float()) < (1.2e-3 if prec == "fp16" else 2e-2)
+    if prec == "fp16":
+        big = ops.linear(_op(a * 300, prec), _op(w * 300, prec), None, precision=prec, out_dtype=torch.float16)
+        assert torch.isfinite(big.float()).all() and float(big.float().abs().max()) == 65504.0
 
 
 def _attn_ref(qkv, B, S, H, mask):
@@ -123,7 +150,7 @@ def _attn_ref(qkv, B, S, H, mask):
     return o.transpose(1, 2).reshape(B * S, D).float()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("B,S,H,kind", [(2, 37, 2, "prev"), (1, 200, 3, "causal"), (1, 565, 12, "prev"), (2, 128, 2, "none"),
                                         (1, 300, 2, "causal")])
 def test_attention_masks(prec, B, S, H, kind):
@@ -142,13 +169,12 @@ def test_attention_masks(prec, B, S, H, kind):
     if prec == "fp32":
         out = ops.attention_fp32(qkv, B, S, H, mk, torch.tensor(list(pr) or [0], dtype=torch.int32, device="cuda"))
     else:
-        out = ops.attention_tc(qkv, B, S, H, mk, pr, prec,
-                               out_dtype=torch.bfloat16 if prec == "bf16" else torch.float32).float()
+        out = ops.attention_tc(qkv, B, S, H, mk, pr, prec, out_dtype=H16.get(prec, torch.float32)).float()
     e = relerr(out, ref)
-    assert e < TOL[prec], f"{prec} {kind} S={S}: {e}"
+    assert e < TOL[prec] * (1.5 if prec == "fp16" else 1), f"{prec} {kind} S={S}: {e}"  # fp16: + the 16-bit output rounding
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("kind", ["prev", "causal"])
 def test_attention_large_score_range_exercises_lazy_rescale(prec, kind):
     """Scores with a wide dynamic range force the running-max reference to move many times (the O *= alpha path
@@ -167,13 +193,13 @@ def test_attention_large_score_range_exercises_lazy_rescale(prec, kind):
     else:
         mask, mk, pr = O.build_attention_mask(S, "causal"), ops.MASK_CAUSAL, ()
     ref = _attn_ref(qkv, B, S, H, mask)
-    out = ops.attention_tc(qkv, B, S, H, mk, pr, prec, out_dtype=torch.bfloat16 if prec == "bf16" else torch.float32).float()
+    out = ops.attention_tc(qkv, B, S, H, mk, pr, prec, out_dtype=H16.get(prec, torch.float32)).float()
     e = relerr(out, ref)
-    assert e < (3e-3 if prec == "tf32" else 3e-2), f"{prec} {kind}: {e}"
+    assert e < (3e-2 if prec == "bf16" else 3e-3), f"{prec} {kind}: {e}"
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
-@pytest.mark.parametrize("B,S,H", [(2, 37, 2), (1, 565, 12), (3, 128, 4)])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "fp16"])
+@pytest.mark.parametrize("B,S,H", [(2, 37, 2), (1, 565, 12), (3, 128, 4), (3, 515, 12), (2, 700, 12)])
 def test_fused_qkv_projection_scatter_matches_split(prec, B, S, H):
     """mmvid_linear_qkv (GEMM epilogue writes Q,K,V^T in attention layout) vs linear + qkv_split."""
     ops = _ops()
@@ -184,12 +210,9 @@ def test_fused_qkv_projection_scatter_matches_split(prec, B, S, H):
     b = torch.randn(3 * D, generator=g).cuda()
     ref = F.linear(x.double(), w.double(), b.double()).float().view(B, S, 3, H, 64)
     bufs = ops.alloc_qkv_buffers(B, H, S, prec, "cuda")
-    if prec == "bf16":
-        ops.linear_qkv(x.bfloat16(), w.bfloat16(), b, bufs, B, S, H, prec)
-    else:
-        ops.linear_qkv(x, w, b, bufs, B, S, H, prec)
+    ops.linear_qkv(_op(x, prec), _op(w, prec), b, bufs, B, S, H, prec)
     q, k, vt = [t.float() for t in bufs]
-    tol = TOL[prec]
+    tol = TOL[prec] * (1.5 if prec == "fp16" else 1)
     assert relerr(q[:, :, :S], ref[:, :, 0].permute(0, 2, 1, 3)) < tol
     assert relerr(k[:, :, :S], ref[:, :, 1].permute(0, 2, 1, 3)) < tol
     assert relerr(vt[:, :, :, :S], ref[:, :, 2].permute(0, 2, 3, 1)) < tol
@@ -395,7 +418,7 @@ def test_fused_qkv_on_the_cta_pair_kernel_is_identical_to_the_single_cta_kernel(
     assert float(q[:, :, S:].abs().max()) == 0 and float(k[:, :, S:].abs().max()) == 0 and float(vt[:, :, :, S:].abs().max()) == 0
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("poly", ["0", "2", "4"])
 def test_attention_fma_pipe_exponentials_agree_with_fp64(monkeypatch, prec, poly):
     """The rotating-score-buffer kernel with 0 / 2 / 4 of every 8 exponentials on the FMA pipe (MMVID_ATT_POLY), both masks,
@@ -406,12 +429,12 @@ def test_attention_fma_pipe_exponentials_agree_with_fp64(monkeypatch, prec, poly
     g = torch.Generator().manual_seed(S)
     qkv = torch.randn(B * S, 3 * H * 64, generator=g).cuda()
     monkeypatch.setenv("MMVID_ATT_POLY", poly)
-    odt = torch.bfloat16 if prec == "bf16" else torch.float32
+    odt = H16.get(prec, torch.float32)
     for kind, mk, rows in (("mask_prev", ops.MASK_PREV, (400, 401)), ("causal", ops.MASK_CAUSAL, ())):
         mask = O.build_attention_mask(S, kind, rows) if kind == "mask_prev" else O.build_attention_mask(S, "causal")
         ref = _attn_ref(qkv, B, S, H, mask)
         out = ops.attention_tc(qkv, B, S, H, mk, rows, prec, out_dtype=odt).float()
-        assert relerr(out, ref) < TOL[prec], f"{prec} poly {poly} {kind}"
+        assert relerr(out, ref) < TOL[prec] * (1.5 if prec == "fp16" else 1), f"{prec} poly {poly} {kind}"
 
 
 def test_groupnorm_streaming_kernel_exact_and_fast_swish():
