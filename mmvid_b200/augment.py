@@ -43,6 +43,35 @@ def _affine(frame, angle_deg=30, trans=0.1, scale=0.1):
     return F.grid_sample(x, grid, padding_mode="reflection", align_corners=False)[0]
 
 
+def warp_video_with_color(video):
+    """dalle_bert.py:140-158: one colour shift per clip (all channels or one of R / G / B), the same for every frame of
+    the clip.  video [n, t, 3, h, w] in [0, 1].  RNG order per clip as in the reference: torch.rand(1) (CPU generator), then
+    python random.randint(0, 3)."""
+    out = []
+    for n in range(video.shape[0]):
+        x = video[n]
+        shift = (torch.rand(1) - 0.5).to(x.device)
+        which = random.randint(0, 3)
+        delta = torch.zeros_like(x)
+        if which == 0:
+            delta += shift
+        else:
+            delta[:, which - 1] += shift
+        out.append(torch.clamp(x + delta, 0, 1))
+    return torch.stack(out)
+
+
+def augment_visual(visual, visual_aug_mode):
+    """BERT.forward's training-time visual-control augmentation (dalle_bert.py:940-944): with probability 0.9 every
+    control frame but the first of each sample gets the clip's colour shift ('motion_color')."""
+    # any other mode is silently ignored by the reference, and draws nothing (`==` short-circuits the `and`)
+    if visual_aug_mode == "motion_color" and random.random() < 0.9:
+        out = visual.detach().clone()
+        out[:, 1:] = warp_video_with_color(visual[:, 1:])
+        return out
+    return visual
+
+
 def warp(x, vid_strategy_prob=(0.25, 0.25, 0.25, 0.25)):
     """x [b,t,c,h,w] -> corrupted copy: 0 frame from another clip, 1 shuffled frames, 2 colour shift, 3 affine warp."""
     b, t = x.shape[:2]

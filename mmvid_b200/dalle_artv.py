@@ -215,8 +215,9 @@ class DALLE(nn.Module):
             f"the length {text.shape[-1]} of the text tokens you passed in does not have the correct length ({self.text_seq_len})"
         if return_loss:
             raise NotImplementedError("training losses / backward are scheduled after the inference path")
-        if visual_aug_mode is not None:
-            raise NotImplementedError
+        if visual_aug_mode is not None and exists(visual) and not is_empty(visual):
+            from .augment import augment_visual
+            visual = augment_visual(visual, visual_aug_mode)  # dalle_artv.py:460-463
         B, dev = text.shape[0], text.device
         with torch.no_grad():
             visual_ids = self._visual_ids(visual, B, dev, erase_visual, erase_visual_half, vc_mode, face_mode)

@@ -296,7 +296,8 @@ class BERT(nn.Module):
         if self.num_visuals > 0:
             if exists(visual) and len(visual):
                 if visual_aug_mode is not None:
-                    raise NotImplementedError("visual_aug_mode is a training-time augmentation")
+                    from .augment import augment_visual
+                    visual = augment_visual(visual, visual_aug_mode)  # dalle_bert.py:940-944
                 visual_ids = self.get_image_tokens(visual, insert_sep=self.insert_sep, which_vae="cvae")
                 if erase_visual:
                     visual_ids = self.random_erase_codebook(visual_ids, self._visual_eraser(), erase_visual_half)
@@ -311,8 +312,13 @@ class BERT(nn.Module):
         if not return_loss:
             return control
         # ------------------------------------------------------------------ training losses (dalle_bert.py:980-1127)
+        text_neg_ids = None
         if negvc:
-            raise NotImplementedError("negvc (explicit negative text/visual control) is not on the default training path")
+            # dalle_bert.py:909-935, 974-975: the negative control sequence is [REL] + text_neg + [ST1][VID]; the reference
+            # never adds a visual segment to it (visual_neg is accepted and ignored), so with visual control it is shorter
+            # than the positive one and the mask rows keep their absolute positions (clip_model.py:217-221 slices the mask).
+            assert text_neg is not None and text_neg.shape == text.shape, "negvc=True needs text_neg shaped like text"
+            text_neg_ids = text_neg
         target_orig = target
         target_ids = self.get_image_tokens(target)
         mask1, not_fully_masked = self._sample_msm_masks(B, dev, msm_strategy_prob, msm_bernoulli_prob, pc_prob)
@@ -321,7 +327,8 @@ class BERT(nn.Module):
             from .augment import warp
             target_warp_ids = self.get_image_tokens(warp(target_orig, vid_strategy_prob))
         return self._losses(text, visual_ids, target_ids, mask1, not_fully_masked, rel=rel, vid=vid,
-                            rel_no_fully_masked=rel_no_fully_masked, target_warp_ids=target_warp_ids)
+                            rel_no_fully_masked=rel_no_fully_masked, target_warp_ids=target_warp_ids,
+                            text_neg=text_neg_ids)
 
     # ------------------------------------------------------------------------------------------ training internals
     def _sample_msm_masks(self, B, dev, strategy_prob, bernoulli_prob, pc_prob):
@@ -349,7 +356,7 @@ class BERT(nn.Module):
             masks.append(m)
         return torch.stack(masks, 0) == 1, nfm
 
-    def _embed_train(self, text, visual_ids, target_ids_masked):
+    def _embed_train(self, text, visual_ids, target_ids_masked, with_visual=True, with_target=True):
         """Residual stream [B,S,D] with autograd to every embedding table (same fused gather kernel as inference)."""
         from .autograd import EmbedFn
         B, dev, D = text.shape[0], text.device, self.dim
@@ -361,12 +368,14 @@ class BERT(nn.Module):
 
         parts = [seg(self.special_emb.weight, self.special_pos_emb.weight, None, self._const_ids([0], dev).expand(B, 1).contiguous()),
                  seg(self.text_emb.weight, None, self.text_pos_emb.weight, text, (0, self.num_text_tokens - self.text_seq_len))]
-        if self.num_visuals > 0:
+        if self.num_visuals > 0 and with_visual:
             table = self.visual_emb.weight if self.visual_emb is not None else self.image_emb.weight
             parts.append(seg(table, None, self._axial_pos(self.visual_pos_emb), visual_ids))
         parts.append(seg(self.special_emb.weight, self.special_pos_emb.weight, None,
                          self._const_ids([1, 2], dev).expand(B, 2).contiguous()))
         control = torch.cat(parts, dim=1)
+        if not with_target:
+            return control, None
         target = seg(self.image_emb.weight, None, self._axial_pos(self.target_pos_emb), target_ids_masked)
         return control, target
 
@@ -415,7 +424,7 @@ class BERT(nn.Module):
         return LinearFn.apply(h, seq[1].weight, seq[1].bias, ACT_NONE, prec)
 
     def _losses(self, text, visual_ids, target_ids, mask1, not_fully_masked, rel=False, vid=False,
-                rel_no_fully_masked=False, target_warp_ids=None, swap_perm=None):
+                rel_no_fully_masked=False, target_warp_ids=None, swap_perm=None, text_neg=None):
         """MSM / REL / VID losses (dalle_bert.py:1030-1127) for given masks; autograd flows to all trainable params."""
         from .autograd import cross_entropy_selected
         B, dev, D = text.shape[0], text.device, self.dim
@@ -431,8 +440,12 @@ class BERT(nn.Module):
         denom = max(1.0, float(not_fully_masked.sum()))
         if rel:
             assert B >= 2 and B % 2 == 0, "REL needs an even batch (control sequences are swapped between halves)"
-            perm = swap_perm if swap_perm is not None else torch.cat((torch.arange(B // 2, B), torch.arange(0, B // 2))).to(dev)
-            out_neg = self._transformer_train(torch.cat((control[perm], target_emb), dim=1))
+            if text_neg is not None:  # negvc: explicit negative text, no visual segment (dalle_bert.py:1047-1055)
+                control_neg = self._embed_train(text_neg, None, tgt_masked, with_visual=False, with_target=False)[0]
+            else:
+                perm = swap_perm if swap_perm is not None else torch.cat((torch.arange(B // 2, B), torch.arange(0, B // 2))).to(dev)
+                control_neg = control[perm]
+            out_neg = self._transformer_train(torch.cat((control_neg, target_emb), dim=1))
             lp = self._head_train(out[:, self.rel_tok_index], self.to_logits_rel).squeeze(-1)
             ln = self._head_train(out_neg[:, self.rel_tok_index], self.to_logits_rel).squeeze(-1)
             if rel_no_fully_masked:

@@ -102,6 +102,52 @@ def test_reference_train_call_signature_and_optimizer_step(fused):
     assert all(np.isfinite(hist)) and hist[-1] < hist[0]
 
 
+def test_shipped_training_flags_negvc_and_visual_aug_mode_run_and_match_oracle_losses():
+    """scripts/mmvoxceleb/image_and_video/train.sh passes --visual_aug_mode motion_color; --negvc feeds an explicit negative
+    text (train.py:259-262, 312-314).  negvc: the REL negative is [REL] + text_neg + [ST1][VID] WITHOUT a visual segment
+    (dalle_bert.py:909-935, 974-975), checked here against a direct evaluation of that sequence."""
+    import random
+    cfg = BERT_CASES["bert_tiny"]
+    model, _ = build_bert(cfg, precision="fp32")
+    model.train()
+    B = 2
+    text = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], 1).cuda()
+    text_neg = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], 9).cuda()
+    visual = synth.synth_frames(B, cfg["num_visuals"], cfg["image_size"], 2).cuda()
+    frames = synth.synth_frames(B, cfg["num_targets"], cfg["image_size"], 3).cuda()
+    kw = dict(target=frames, return_loss=True, rel=True, vid=True, msm_strategy_prob=np.array([1.0, 0, 0, 0]),
+              msm_bernoulli_prob=[0.4, 0.6], vid_strategy_prob=np.array([0.25] * 4))
+
+    def run(**extra):
+        np.random.seed(3); random.seed(3); torch.manual_seed(3)
+        return model(text, visual=visual, **kw, **extra)
+
+    base = run()
+    neg = run(negvc=True, text_neg=text_neg, visual_neg=visual)
+    aug = run(visual_aug_mode="motion_color")
+    for l in (*base, *neg, *aug):
+        assert torch.isfinite(l)
+    assert float(neg[0]) == float(base[0]) and float(neg[2]) == float(base[2])  # MSM / VID untouched by negvc
+    assert float(neg[1]) != float(base[1])
+    # direct evaluation of the reference's negative sequence: same masks (same seeds), REL logit of the shorter sequence
+    np.random.seed(3); random.seed(3); torch.manual_seed(3)
+    with torch.no_grad():
+        vis_ids = model.get_image_tokens(visual, which_vae="cvae")
+        tgt_ids = model.get_image_tokens(frames)
+        mask1, _ = model._sample_msm_masks(B, text.device, kw["msm_strategy_prob"], kw["msm_bernoulli_prob"], 0)
+        tgt_masked = torch.where(mask1, tgt_ids, torch.full_like(tgt_ids, 1024))
+        control, temb = model._embed_train(text, vis_ids, tgt_masked)
+        cneg = model._embed_train(text_neg, None, tgt_masked, with_visual=False, with_target=False)[0]
+        assert cneg.shape[1] == 1 + cfg["text_seq_len"] + 2
+        lp = model._head_train(model._transformer_train(torch.cat((control, temb), 1))[:, 0], model.to_logits_rel).squeeze(-1)
+        ln = model._head_train(model._transformer_train(torch.cat((cneg, temb), 1))[:, 0], model.to_logits_rel).squeeze(-1)
+        bce = torch.nn.functional.binary_cross_entropy_with_logits
+        want = bce(lp, torch.ones(B, device="cuda")) + bce(ln, torch.zeros(B, device="cuda"))
+    assert abs(float(neg[1]) - float(want)) < 1e-5 * max(1.0, abs(float(want)))
+    (7 * neg[0] + 0.5 * neg[1] + 0.5 * neg[2]).backward()
+    assert model.text_emb.weight.grad is not None and float(model.text_emb.weight.grad.abs().sum()) > 0
+
+
 @pytest.mark.parametrize("kind,wd", [("adam", 0.0), ("adam", 0.01), ("adamw", 0.05)])
 def test_fused_adam_and_clip_match_torch_optimisers(kind, wd):
     """train.py:322-325 step: clip_grad_norm_ + Adam/AdamW, multi-tensor kernels vs torch's own CPU optimisers

@@ -145,20 +145,22 @@ def test_bench_stdout_carries_only_the_json_line():
 def test_gemm_tile_picker_on_the_benchmark_shapes():
     """Host-only dispatch of mmvid_linear (no GPU needed: 148 SMs are assumed without a device).  2000 + BN = CTA-pair kernel
     with a 256 x BN tile, 1000 + BN = single-CTA kernel.  The benchmark's layers must land on the tiles the pipeline traces
-    selected (profiles/r1_g_gemm_pipeline.md); small problems stay on small single-CTA tiles; bf16 OUTPUTS stay single-CTA
-    (their epilogue is not a TMA store yet)."""
+    selected (profiles/r1_g_gemm_pipeline.md); small problems stay on small single-CTA tiles; the 16-bit kinds (bf16 / fp16
+    operands, 16-bit or fp32 results through TMA stores) take the widest CTA-pair tile that quantises well over 74 pairs."""
     from mmvid_b200 import _lib as L
     lib = L.load()
-    TF32, BF16, F32, B16 = L.TF32, L.BF16, L.DT_F32, L.DT_BF16
+    TF32, BF16, F16, F32, B16, H16 = L.TF32, L.BF16, L.F16, L.DT_F32, L.DT_BF16, L.DT_F16
     pick = lib.mmvid_debug_pick_tile
     M = 4 * 2115
     assert pick(M, 3072, 768, TF32, F32) == 2256       # c_fc
     assert pick(M, 768, 3072, TF32, F32) == 2192       # c_proj: 136 tiles of 256 x 192 for 74 pairs instead of 102 of 256 x 256
     assert pick(M, 768, 768, TF32, F32) == 2192        # out_proj
     assert pick(4 * 2048, 1024, 768, TF32, F32) == 2256  # logits head
-    assert pick(M, 3072, 768, BF16, B16) == 1128       # bf16 output, short K: single CTA
-    assert pick(M, 768, 3072, BF16, B16) == 2128       # bf16 output, long K: 256 x 128 pair (deeper TMA ring)
-    assert pick(M, 768, 3072, BF16, F32) == 2192       # bf16 operands, fp32 residual stream
+    for kind, dt16 in ((BF16, B16), (F16, H16)):
+        assert pick(M, 3072, 768, kind, dt16) == 2256      # c_fc, 16-bit GELU output
+        assert pick(M, 768, 3072, kind, F32) == 2192       # c_proj: 16-bit operands, fp32 residual stream
+        assert pick(M, 768, 768, kind, F32) == 2192        # out_proj
+        assert pick(4 * 2048, 1024, 768, kind, F32) == 2256  # logits head
     assert pick(130, 192, 128, TF32, F32) == 1064      # tiny problem: most CTAs
     assert pick(0, 192, 128, TF32, F32) // 1000 == 1
 
@@ -190,3 +192,39 @@ def test_fma_pipe_exp2_polynomial_accuracy_claims():
     # masked keys (-inf) and very negative scores give a tiny positive number instead of an exponent-field borrow
     edge = exp2_poly(np.array([-np.inf, -1e30, -126.0, -125.7], dtype=f32), 4)
     assert np.all(edge >= 0) and np.all(edge < 3e-38)
+
+
+def test_visual_aug_motion_color_follows_the_reference_rng_order_and_semantics():
+    """augment_visual = dalle_bert.py:940-944 + warp_video_with_color (:140-158): python random gates (p = 0.9), then per clip
+    torch.rand(1) and random.randint(0, 3); first control frame untouched; other modes are ignored without drawing."""
+    import random
+    import torch
+    from mmvid_b200.augment import augment_visual
+    g = torch.Generator().manual_seed(0)
+    visual = torch.rand(3, 4, 3, 8, 8, generator=g)
+    random.seed(5)
+    torch.manual_seed(5)
+    out = augment_visual(visual, "motion_color")
+    # restatement with the reference's own statements
+    random.seed(5)
+    torch.manual_seed(5)
+    exp = visual
+    if random.random() < 0.9:
+        exp = visual.detach().clone()
+        clips = []
+        for n in range(visual.shape[0]):
+            x = visual[n, 1:]
+            c_shift = torch.rand(1) - 0.5
+            m = torch.zeros_like(x)
+            num = random.randint(0, 3)
+            if num == 0:
+                m += c_shift
+            else:
+                m[:, num - 1] += c_shift
+            clips.append(torch.clamp(x + m, 0, 1))
+        exp[:, 1:] = torch.stack(clips)
+    assert torch.equal(out, exp)
+    assert torch.equal(out[:, 0], visual[:, 0]) and not torch.equal(out[:, 1:], visual[:, 1:])
+    state = random.getstate()
+    assert augment_visual(visual, "something_else") is visual and random.getstate() == state
+    assert augment_visual(visual, None) is visual
