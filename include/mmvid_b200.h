@@ -156,6 +156,23 @@ int mmvid_artv_decode_fused(const mmvid_decode_layer* host_layers, int n_layers,
                                  const float* head_b, float* logits, int n_logits, int B, int D, int H, int S_max,
                                  int pos, mmvid_stream_t stream);
 
+/* Fourth generation (decode_stream.cu): ONE persistent cooperative launch per token.  Every CTA owns a fixed column slice of
+ * every weight matrix and streams its slabs of the next phases into a shared-memory ring with bulk async copies while the
+ * current phase computes; phases are separated by a light grid barrier.  Weights and K/V caches are 16-bit (f16 != 0: fp16,
+ * else bf16), accumulation / LayerNorm / softmax / residual stream fp32.  ws: mmvid_artv_decode_stream_workspace_floats
+ * floats, ZERO-INITIALISED once by the caller.  Returns 1 when the shape does not fit the kernel's shared-memory plan
+ * (callers fall back to mmvid_artv_decode_fused on fp32 weights). */
+typedef struct {
+  const float *ln1_w, *ln1_b, *in_b, *out_b, *ln2_w, *ln2_b, *fc_b, *proj_b;
+  const void *in_w, *out_w, *fc_w, *proj_w; /* 16-bit, [N, K] row-major */
+  void *kcache, *vcache;                    /* [B, H, S_max, 64] 16-bit */
+} mmvid_decode_layer16;
+long long mmvid_artv_decode_stream_workspace_floats(int B, int D, int H);
+int mmvid_artv_decode_stream(const mmvid_decode_layer16* host_layers, int n_layers, float* h, float* ws,
+                             const float* head_ln_w, const float* head_ln_b, const void* head_w16, const float* head_b,
+                             float* logits, int n_logits, int B, int D, int H, int S_max, int pos, int f16,
+                             mmvid_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K14  VQ nearest-codeword lookup (taming/modules/vqvae/quantize.py:302-311):
  *   d[t,j] = (sum z_t^2 + sum e_j^2) - 2 z_t.e_j   in fp32, this association; idx[t] = argmin_j (lowest index wins)

@@ -41,6 +41,11 @@ class DecodeLayer(C.Structure):
                                   "proj_w", "proj_b", "kcache", "vcache")]
 
 
+class DecodeLayer16(C.Structure):
+    _fields_ = [(n, _p) for n in ("ln1_w", "ln1_b", "in_b", "out_b", "ln2_w", "ln2_b", "fc_b", "proj_b", "in_w", "out_w",
+                                  "fc_w", "proj_w", "kcache", "vcache")]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("p", _p), ("g", _p), ("m", _p), ("v", _p), ("n", _ll), ("skipped", _ll)]
 
@@ -75,6 +80,8 @@ SIGNATURES = {
     "mmvid_artv_decode_step": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mmvid_artv_decode_persistent": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mmvid_artv_decode_fused": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mmvid_artv_decode_stream_workspace_floats": (_ll, [_i, _i, _i]),
+    "mmvid_artv_decode_stream": (_i, [C.POINTER(DecodeLayer16), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mmvid_vq_argmin": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),

@@ -136,10 +136,13 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
   // would see every OTHER completion - always the same parity - and mistake the previous phase for its own.
   uint64_t* s_full = bars + 9;    // [6] QK(n) landed in X(n mod 3)
   uint64_t* p_ready = bars + 15;  // [6] P(n) written over it (count 4: one arrival per warp)
-  uint64_t* o_full = bars + 21;   // [2] per query tile: PV(n) retired
-  uint64_t* all_done = bars + 23;
-  uint64_t* tok = bars + 24;      // [2][4] MUFU ping-pong token per query tile and SM sub-partition (see softmax warps)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
+  // o_full[g][j & 1]: PV of query tile g, key step j retired.  TWO barriers per tile (even / odd key steps): the softmax
+  // group only looks at them on the rare rescale path, by which time a single barrier could be one OR two phases ahead
+  // of the last phase the group saw - indistinguishable for a parity wait.  Each of the two is at most one phase ahead.
+  uint64_t* o_full = bars + 21;   // [2][2]
+  uint64_t* all_done = bars + 25;
+  uint64_t* tok = bars + 26;      // [2][4] MUFU ping-pong token per query tile and SM sub-partition (see softmax warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 512 + 1023) & ~(uintptr_t)1023);
   constexpr int ESZ = TF32 ? 4 : 2;
   constexpr int BKE = 128 / ESZ;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
-      mbar_init(&o_full[i], 1);
+      mbar_init(&o_full[2 * i], 1); mbar_init(&o_full[2 * i + 1], 1);
     }
     for (int i = 0; i < 6; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
     for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
             mma_ts<TF32>(o, x + kb * 32 + kk * 8, vd + (uint64_t)(kb * (HD * 128 / 16) + kk * 2), idesc_pv,
                          (j != 0 || (kb | kk) != 0) ? 1u : 0u);
         tc_commit(&v_empty[st]);
-        tc_commit(&o_full[g]);
+        tc_commit(&o_full[2 * g + (j & 1)]);
       };
       if (warp == 1) {  // prologue: the first three QK^T fill the three score buffers
         mbar_wait(q_full, 0);
@@ -377,13 +380,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
       if (__any_sync(0xffffffffu, resc)) {
         // rare path: O_g *= alpha in TMEM (alpha = 1 for rows that keep their reference).  PV of this tile's previous
         // step must have retired; PV of this step is not issued before p_ready below.
-        // A parity wait only tells phases apart modulo 2, and this group has not looked at o_full since its last rescale.
-        // s_full(n) observed => QK(n-3) retired => PV(n-6) = PV_g(j-3), issued earlier by the same thread, retired: the
-        // barrier is at most two phases behind, so waiting for phase j-2 and then for phase j-1 is unambiguous.  (A single
-        // wait for j-1 passes at once while PV_g(j-2) is still outstanding - e.g. its V tile is late - and the rescale
-        // would then race the accumulating MMA.)
-        if (j >= 2) mbar_wait(&o_full[g], (uint32_t)j & 1);
-        mbar_wait(&o_full[g], (uint32_t)(j & 1) ^ 1);
+        // PV_g(j-1) must have retired before O is read-modify-written.  It commits to barrier (j-1) & 1 of this tile as that
+        // barrier's phase (j-1) >> 1.  s_full(n) observed => QK(n-3) retired => PV(n-6) = PV_g(j-3), issued earlier by the
+        // same thread, retired: the barrier has completed every phase before this one, and cannot be past it (PV_g(j+1)
+        // needs P of this very step), so the parity wait is unambiguous however long ago the group last looked.
+        mbar_wait(&o_full[2 * g + ((j - 1) & 1)], (uint32_t)((j - 1) >> 1) & 1u);
         tc_fence_after();
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {

@@ -268,8 +268,10 @@ PFN_encodeTiled get_encode_fn();
 constexpr int DT_F32_EXACT = 100;
 
 // rank-`rank` tensor map, innermost dimension first.  strides_bytes has rank-1 entries (dims 1..rank-1).
+// swizzle128 = false: SWIZZLE_NONE (dense box rows; used where the inner box is narrower than the 128-byte swizzle span).
 int make_tensor_map(CUtensorMap* out, const void* base, int dtype /*MMVID_DT_*/, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr,
+                    bool swizzle128 = true);
 
 }  // namespace tc
 }  // namespace mmvid

@@ -3,7 +3,8 @@
 // In the TMA-store epilogues a lane owns one output row of its warp's 32 x 32 accumulator chunks.  With 16-bit results
 // two neighbouring chunks (64 columns) make one 128-byte row: both are packed in registers, written once to the warp's
 // 4 KB staging buffer in the SWIZZLE_128B layout and leave as ONE {64 x 32} bulk store; a lone chunk (odd chunk count
-// of the 192-wide tile, 64-wide tiles, the last columns of N) leaves as a {32 x 32} store with 64-byte rows.
+// of the 192-wide tile, 64-wide tiles, the last columns of N) leaves as a {32 x 32} store with dense 64-byte rows
+// through a SWIZZLE_NONE tensor map (a few bank conflicts on a rare path).
 #pragma once
 #include "tc_common.cuh"
 
@@ -12,34 +13,6 @@ namespace tc {
 
 __device__ __forceinline__ void sts128_u32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-// pack one 32-float chunk of this lane's row into 16 words (bf16 or fp16 pairs)
-__device__ __forceinline__ void pack_chunk_h16(const float (&o)[32], uint32_t (&pk)[16], int f16) {
-  if (f16) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pk[i] = pack_h16<true>(o[2 * i], o[2 * i + 1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pk[i] = pack_h16<false>(o[2 * i], o[2 * i + 1]);
-  }
-}
-
-// Stage chunk `slot` (0 | 1) of a 2-chunk group: 128-byte rows, 16-byte unit u of row r at unit u ^ (r & 7).
-__device__ __forceinline__ void stage_h16_pair(uint32_t st_base, int lane, int slot, const uint32_t (&pk)[16]) {
-  const uint32_t row = st_base + (uint32_t)(lane * 128);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    sts128_u32(row + (uint32_t)((((slot * 4 + j) ^ (lane & 7))) * 16), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-}
-// Stage a lone chunk: 64-byte rows in a SWIZZLE_128B box, i.e. byte offset x of the dense box lives at
-// x ^ (((x >> 7) & 7) << 4).
-__device__ __forceinline__ void stage_h16_single(uint32_t st_base, int lane, const uint32_t (&pk)[16]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t lin = (uint32_t)(lane * 64 + j * 16);
-    sts128_u32(st_base + (lin ^ (((lin >> 7) & 7u) << 4)), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-  }
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {

@@ -36,7 +36,7 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, bool swizzle128) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return fail(MMVID_ECUDA, "cuTensorMapEncodeTiled entry point unavailable%s");
   cuuint64_t gdim[5], gstr[5];
@@ -52,7 +52,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, con
                                  : dtype == MMVID_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                  : (dtype == DT_F32_EXACT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MMVID_ECUDA, "cuTensorMapEncodeTiled failed (%s) code %lld", "", (long long)r);
   return MMVID_OK;
 }
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 const uint32_t u2 = pack_h16_rt(o[8 * j + 4], o[8 * j + 5], f16), u3 = pack_h16_rt(o[8 * j + 6], o[8 * j + 7], f16);
                 uint32_t addr;
                 if (nvalid == 2) addr = st_row + (uint32_t)(((cc * 4 + j) ^ (lane & 7)) * 16);
-                else { const uint32_t lin = (uint32_t)(lane * 64 + j * 16); addr = st_base + (lin ^ (((lin >> 7) & 7u) << 4)); }
+                else addr = st_base + (uint32_t)(lane * 64 + j * 16);  // lone chunk: dense 64-byte rows (SWIZZLE_NONE map)
                 sts128_u32(addr, u0, u1, u2, u3);
               }
               continue;
@@ -651,7 +652,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, EpiArgs e, cudaStream
       uint32_t box[2] = {64, 32}, box1[2] = {32, 32};
       int rc = make_tensor_map(&tmC, e.C, dt, 2, dims, str, box);
       if (rc) return rc;
-      rc = make_tensor_map(&tmC1, e.C, dt, 2, dims, str, box1);
+      rc = make_tensor_map(&tmC1, e.C, dt, 2, dims, str, box1, nullptr, /*swizzle128=*/false);
       if (rc) return rc;
     } else {
       uint32_t box[2] = {32, 32};

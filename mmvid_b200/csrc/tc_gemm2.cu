@@ -312,7 +312,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
                 const uint32_t u2 = pack_h16_rt(o[8 * j + 4], o[8 * j + 5], f16), u3 = pack_h16_rt(o[8 * j + 6], o[8 * j + 7], f16);
                 uint32_t addr;
                 if (nvalid == 2) addr = st_row + (uint32_t)(((cc * 4 + j) ^ (lane & 7)) * 16);
-                else { const uint32_t lin = (uint32_t)(lane * 64 + j * 16); addr = st_base + (lin ^ (((lin >> 7) & 7u) << 4)); }
+                else addr = st_base + (uint32_t)(lane * 64 + j * 16);  // lone chunk: dense 64-byte rows (SWIZZLE_NONE map)
                 sts128_u32(addr, u0, u1, u2, u3);
               }
               continue;
@@ -548,7 +548,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStre
       uint32_t box[2] = {64, 32}, box1[2] = {32, 32};
       int rc = make_tensor_map(&tmC, e.C, dt, 2, dims, str, box);
       if (rc) return rc;
-      rc = make_tensor_map(&tmC1, e.C, dt, 2, dims, str, box1);
+      rc = make_tensor_map(&tmC1, e.C, dt, 2, dims, str, box1, nullptr, /*swizzle128=*/false);
       if (rc) return rc;
     } else {
       uint32_t box[2] = {32, 32};

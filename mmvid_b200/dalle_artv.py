@@ -267,9 +267,20 @@ class DALLE(nn.Module):
         S_max = P + self.target_seq_len
         x = torch.empty(B, P, D, device=dev, dtype=torch.float32)
         ops.embed_gather(x, self._prefix_segments(text, visual_ids))
+        # ---- decode implementation.  'stream' (default in the tensor-core precisions, B <= 8): ONE persistent launch per
+        # token on 16-bit weights and a 16-bit K/V cache (decode_stream.cu).  fp32 precision keeps the fp32 kernels that
+        # reproduce the reference's sampled ids bit for bit: 'fused' (5 PDL-chained launches / layer, decode_pdl.cu),
+        # 'persistent' (cooperative, fp32), 'native' (8 launches / layer).
+        prec = PRECISIONS[self.precision]
+        impl = os.environ.get("MMVID_ARTV_DECODE", getattr(self, "decode_impl", None) or ("fused" if prec == 0 else "stream"))
+        stream = impl == "stream" and B <= 8 and prec != 0
+        if impl == "stream" and not stream:
+            impl = "fused"
+        h16 = torch.bfloat16 if prec == 2 else torch.float16  # tf32 mode: fp16 copies carry the same 10-bit mantissa
+        cache_dt = h16 if stream else torch.float32
         # ---- prefill: full causal forward over the prefix, K/V of every layer captured into the caches
-        kc = [torch.zeros(B, H, S_max, 64, device=dev, dtype=torch.float32) for _ in blocks]
-        vc = [torch.zeros(B, H, S_max, 64, device=dev, dtype=torch.float32) for _ in blocks]
+        kc = [torch.zeros(B, H, S_max, 64, device=dev, dtype=cache_dt) for _ in blocks]
+        vc = [torch.zeros(B, H, S_max, 64, device=dev, dtype=cache_dt) for _ in blocks]
         hid = self.transformer(x, kv_out=(kc, vc))
         lo = self.num_control_tokens
         logits = self._head_rows(hid[:, -1].contiguous(), lo, lo + self.num_image_tokens)
@@ -280,7 +291,29 @@ class DALLE(nn.Module):
             raise NotImplementedError("filter_thres that prunes inside the image vocabulary")
         xt = torch.empty(B, 1, D, device=dev, dtype=torch.float32)
         native = B <= 16
-        if native:
+        ln, lin = self.to_logits[0], self.to_logits[1]
+        if stream:
+            from . import _lib as L
+            lib = L.load()
+            w16 = self.transformer._bf16
+            layers16 = (L.DecodeLayer16 * len(blocks))()
+            keep16 = []
+            for li, blk in enumerate(blocks):
+                e = layers16[li]
+                e.ln1_w, e.ln1_b = blk.ln_1.weight.data_ptr(), blk.ln_1.bias.data_ptr()
+                e.ln2_w, e.ln2_b = blk.ln_2.weight.data_ptr(), blk.ln_2.bias.data_ptr()
+                e.in_b, e.out_b = blk.attn.in_proj_bias.data_ptr(), blk.attn.out_proj.bias.data_ptr()
+                e.fc_b, e.proj_b = blk.mlp.c_fc.bias.data_ptr(), blk.mlp.c_proj.bias.data_ptr()
+                ws_ = [w16.get(q, h16) for q in (blk.attn.in_proj_weight, blk.attn.out_proj.weight, blk.mlp.c_fc.weight,
+                                                 blk.mlp.c_proj.weight)]
+                keep16.append(ws_)
+                e.in_w, e.out_w, e.fc_w, e.proj_w = (t.data_ptr() for t in ws_)
+                e.kcache, e.vcache = kc[li].data_ptr(), vc[li].data_ptr()
+            head_w16 = w16.get(lin.weight, h16)[lo:lo + self.num_image_tokens]
+            head_b = lin.bias.detach()[lo:lo + self.num_image_tokens]
+            ws16 = torch.zeros(int(lib.mmvid_artv_decode_stream_workspace_floats(B, D, H)), device=dev, dtype=torch.float32)
+            logits_buf = torch.empty(B, self.num_image_tokens, device=dev, dtype=torch.float32)
+        if native and not stream:
             from . import _lib as L
             import ctypes as C
             lib = L.load()
@@ -295,13 +328,8 @@ class DALLE(nn.Module):
                 e.proj_w, e.proj_b = blk.mlp.c_proj.weight.data_ptr(), blk.mlp.c_proj.bias.data_ptr()
                 e.kcache, e.vcache = kc[li].data_ptr(), vc[li].data_ptr()
             ws = torch.zeros(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev, dtype=torch.float32)
-            # 'native': 8 launches / layer issued from C (measured 0.88-1.06 ms / token at B = 4);
-            # 'persistent': one cooperative launch per token with grid barriers (opt-in)
-            # 'fused' (default, B <= 8): 5 launches / layer chained with programmatic dependent launch (decode_pdl.cu)
-            impl = os.environ.get("MMVID_ARTV_DECODE", getattr(self, "decode_impl", "fused"))
             persistent = impl == "persistent" and B <= 8 and len(blocks) <= 24
             fused = impl == "fused" and B <= 8
-            ln, lin = self.to_logits[0], self.to_logits[1]
             head_w = lin.weight.detach()[lo:lo + self.num_image_tokens]
             head_b = lin.bias.detach()[lo:lo + self.num_image_tokens]
             logits_buf = torch.empty(B, self.num_image_tokens, device=dev, dtype=torch.float32)
@@ -328,6 +356,17 @@ class DALLE(nn.Module):
                                        pos=pos_table[t:t + 1])])
             h = xt.view(B, D)
             pos = P + t
+            if stream:
+                rc = lib.mmvid_artv_decode_stream(layers16, len(blocks), ops._ptr(h), ops._ptr(ws16), ops._ptr(ln.weight),
+                                                  ops._ptr(ln.bias), ops._ptr(head_w16), ops._ptr(head_b), ops._ptr(logits_buf),
+                                                  self.num_image_tokens, B, D, H, S_max, pos, int(h16 == torch.float16),
+                                                  ops._stream())
+                if rc == 1:
+                    raise RuntimeError("mmvid_artv_decode_stream: shape does not fit the kernel's shared-memory plan; "
+                                       "set decode_impl='fused' with precision='fp32'")
+                L.check(rc, "artv_decode_stream")
+                logits = logits_buf
+                continue
             if native and fused:
                 L.check(lib.mmvid_artv_decode_fused(layers, len(blocks), ops._ptr(h), ops._ptr(ws), ops._ptr(ln.weight),
                                                     ops._ptr(ln.bias), ops._ptr(head_w), ops._ptr(head_b),

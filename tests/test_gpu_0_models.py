@@ -241,6 +241,31 @@ def test_artv_kv_cache_generate_matches_no_cache_oracle_on_gpu(reps, impl):
     assert images.shape[1:] == fx["gen_images"].shape[1:] and images.shape[0] == B
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16", "tf32"])
+@pytest.mark.parametrize("reps", [1, 2, 4])
+def test_artv_streaming_decode_tiny_matches_fp32_kv_cache_path(prec, reps):
+    """decode_stream.cu on the tiny model (D = 128: most CTAs own no column of the narrow matrices, Z = 1 split), B = 2 / 4 /
+    8: per-step image logits against the fp32 fused path fed with the SAME sampled tokens."""
+    cfg = ARTV_CASES["artv_tiny"]
+    B = cfg["batch"] * reps
+    model, _ = build_artv(cfg, precision=prec, sampling_mode="batched")
+    text = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], cfg["seed"]).cuda()
+    visual = synth.synth_frames(B, cfg["num_visuals"], cfg["image_size"], cfg["seed"] + 5).cuda()
+    trace = []
+    torch.manual_seed(3)
+    _, _, toks = model.generate_images(text, visual=visual, return_tokens=True, logits_trace=trace)
+    step = torch.stack(trace, 1)
+    model.precision = model.transformer.precision = "fp32"
+    spec = artv_spec(cfg)
+    full = model(text, visual=visual, target=toks)
+    P = spec.control_seq_len + 1  # <bos> + text + visual tokens: row P - 1 predicts the first image token
+    lo = model.num_control_tokens
+    rows = full[:, P - 1:P - 1 + toks.shape[1], lo:lo + 1024]
+    e = relerr(step, rows)
+    print(f"artv_tiny streaming decode {prec} B={B}: logits relerr vs fp32 full forward {e:.2e}")
+    assert e < (3e-2 if prec == "bf16" else 2e-3)
+
+
 def test_artv_shapeB_kv_cache_first_tokens_match_no_cache_oracle_full_width():
     """BASELINE config 3 at the reference scripts' size (768 x 12, Shape B, batch 4): the first 32 sampled tokens of the
     KV-cache decode against the oracle's full re-forward sampling on the same GPU (fp32 mode, same seed)."""

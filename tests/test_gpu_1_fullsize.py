@@ -151,3 +151,32 @@ def test_artv_shapeA_kv_cache_logits_match_full_causal_forward(impl):
     assert rows.shape == step_logits.shape
     assert relerr(step_logits, rows) < 1e-4
     assert float(full[:, P - 1:, :lo].max()) < -1e30            # text / visual vocabulary masked in image rows
+
+
+@pytest.mark.parametrize("prec,tol", [("fp16", 2e-3), ("tf32", 2e-3), ("bf16", 3e-2)])
+def test_artv_shapeA_streaming_decode_logits_match_full_causal_forward(prec, tol):
+    """The persistent streaming decode kernel (decode_stream.cu: one launch per token, 16-bit weights and K/V cache, fp32
+    accumulation) at Shape A, batch 4 (BASELINE config 3): per-step image logits from the cache against ONE full causal
+    forward of the same model in the same precision over the generated sequence, and against the fp32 path's forward."""
+    cfg = dict(dim=768, layers=12, text_seq_len=64, vocab=49408, num_visuals=1, num_targets=8, image_size=256, seed=35,
+               batch=4)
+    model, _ = build_artv(cfg, precision=prec, sampling_mode="batched")
+    assert getattr(model, "decode_impl", None) is None  # default = streaming kernel in the tensor-core precisions
+    B = cfg["batch"]
+    text = synth.synth_text(B, cfg["text_seq_len"], cfg["vocab"], 4).cuda()
+    visual = synth.synth_frames(B, 1, cfg["image_size"], 6).cuda()
+    trace = []
+    torch.manual_seed(5)
+    _, _, toks = model.generate_images(text, visual=visual, return_tokens=True, logits_trace=trace)
+    assert toks.shape == (B, 2048) and len(trace) == 2048 and int(toks.min()) >= 0 and int(toks.max()) < 1024
+    step_logits = torch.stack(trace, 1)
+    P = cfg["text_seq_len"] + 1 + 256
+    lo = model.num_control_tokens
+    full = model(text, visual=visual, target=toks)
+    rows = full[:, P - 1:P - 1 + 2048, lo:lo + 1024]
+    e_same = relerr(step_logits, rows)
+    model.precision = model.transformer.precision = "fp32"
+    rows32 = model(text[:1], visual=visual[:1], target=toks[:1])[:, P - 1:P - 1 + 2048, lo:lo + 1024]
+    e_fp32 = relerr(step_logits[:1], rows32)
+    print(f"artv shape A streaming decode {prec}: logits relerr vs own full forward {e_same:.2e}, vs fp32 forward {e_fp32:.2e}")
+    assert e_same < tol and e_fp32 < tol
