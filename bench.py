@@ -73,7 +73,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4, help="prompts per GPU per step")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp16", "bf16", "fp32"])
     ap.add_argument("--mp-steps", type=int, default=20)
-    ap.add_argument("--vae-precision", default=None, choices=["tf32", "fp32"],
+    ap.add_argument("--vae-precision", default=None, choices=["fp16", "tf32", "fp32"],
                     help="VQGAN conv precision (default: tf32 tensor cores unless --precision fp32)")
     ap.add_argument("--visuals", type=int, default=0, choices=[0, 1],
                     help="bert/train: number of visual-control frames (1 = SURVEY config 4: cVAE-encoded frame, S=2371)")

@@ -193,9 +193,13 @@ int mmvid_codebook_gather(const int64_t* ids, const float* codebook, float* out,
  *   Downsample (model.py:77-84) = stride 2, pad_t=pad_l=0 with zero fill beyond the right/bottom edge.
  *   in_nchw / out_nchw: read / write NCHW instead (first / last layer of the VQGAN; fuses vae.py:41 `2x-1`
  *   when pre_affine=1 and vae.py:55 clamp(-1,1)*0.5+0.5 when post_clamp=1).
+ *   precision MMVID_TF32 / MMVID_F16: implicit GEMM on tcgen05 whose pixel tiles are fetched by 4-D TMA boxes (halo taps =
+ *   TMA zero fill); MMVID_F16 takes fp16 activations (written by mmvid_groupnorm / mmvid_upsample2x) and fp16 packed
+ *   weights, accumulates in fp32 and writes fp32 (bias / residual fp32): the tf32 mantissa at twice the MMA rate.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  const float* in; const float* w; const float* bias; const float* residual; float* out;
+  const void* in; const void* w; /* fp32; fp16 when precision == MMVID_F16 (tensor-core conv: stride 1, NHWC, Cin % 64 == 0) */
+  const float* bias; const float* residual; float* out;
   int N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, upsample;
   int in_nchw, out_nchw, pre_affine, post_clamp, precision;
 } mmvid_conv_params;
@@ -203,9 +207,10 @@ int mmvid_conv2d(const mmvid_conv_params* p, mmvid_stream_t stream);
 
 /* K11 GroupNorm(32 groups, eps) + optional swish on NHWC (model.py:38-42, 33-35):
  *   stats scratch: mmvid_groupnorm_scratch_floats(N, groups) floats.  out may alias in.
- *   swish: 0 = none, 1 = x*sigmoid(x) with expf and IEEE division (fp32 parity mode), 2 = MUFU ex2 / rcp (~1e-6 relative). */
-int mmvid_groupnorm(const float* in, float* out, const float* gamma, const float* beta, float* stats_scratch,
-                    int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream);
+ *   swish: 0 = none, 1 = x*sigmoid(x) with expf and IEEE division (fp32 parity mode), 2 = MUFU ex2 / rcp (~1e-6 relative).
+ *   out_dtype: MMVID_DT_F32, or MMVID_DT_F16 when the result feeds a kind::f16 conv (then out must not alias in). */
+int mmvid_groupnorm(const float* in, void* out, int out_dtype, const float* gamma, const float* beta,
+                    float* stats_scratch, int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream);
 
 /* size (in floats) of the stats scratch mmvid_groupnorm / mmvid_conv_out_fused need for N images */
 long long mmvid_groupnorm_scratch_floats(int N, int groups);
@@ -221,7 +226,8 @@ int mmvid_conv_out_fused(const float* in, const float* gamma, const float* beta,
                          int post_clamp, mmvid_stream_t stream);
 
 /* nearest x2 upsample NHWC (used only when not fused into the conv) */
-int mmvid_upsample2x(const float* in, float* out, int N, int H, int W, int C, mmvid_stream_t stream);
+int mmvid_upsample2x(const float* in, void* out, int out_dtype /* F32 | F16 */, int N, int H, int W, int C,
+                     mmvid_stream_t stream);
 
 /* elementwise helpers: NCHW<->NHWC transposes of small tensors */
 int mmvid_nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, mmvid_stream_t stream);

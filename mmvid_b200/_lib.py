@@ -85,11 +85,11 @@ SIGNATURES = {
     "mmvid_vq_argmin": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),
-    "mmvid_groupnorm": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "mmvid_groupnorm": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "mmvid_groupnorm_scratch_floats": (_ll, [_i, _i]),
     "mmvid_groupnorm_stats": (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     "mmvid_conv_out_fused": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
-    "mmvid_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "mmvid_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "mmvid_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _p]),
     "mmvid_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _p]),
     "mmvid_softmax_logits": (_i, [_p, _p, _f, _p, _ll, _i, _p]),

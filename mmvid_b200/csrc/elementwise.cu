@@ -307,7 +307,16 @@ extern "C" int mmvid_nhwc_to_nchw(const float* in, float* out, int N, int C, int
   return check_launch("nhwc_to_nchw");
 }
 
-__global__ void upsample2x_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4,
+// four floats -> four fp16 values (round to nearest, saturating) in one 8-byte word
+__device__ __forceinline__ uint2 pack4_f16(float4 v) {
+  uint2 pk;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(v.y), "f"(v.x));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(v.w), "f"(v.z));
+  return pk;
+}
+
+template <bool OUT16>
+__global__ void upsample2x_kernel(const float4* __restrict__ in, void* __restrict__ out, int H, int W, int C4,
                                   long long total) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4);
@@ -315,14 +324,20 @@ __global__ void upsample2x_kernel(const float4* __restrict__ in, float4* __restr
     const int x = (int)(p % (2 * W)); p /= (2 * W);
     const int y = (int)(p % (2 * H));
     const long long n = p / (2 * H);
-    out[i] = in[((n * H + (y >> 1)) * W + (x >> 1)) * C4 + c];
+    const float4 v = in[((n * H + (y >> 1)) * W + (x >> 1)) * C4 + c];
+    if (OUT16) reinterpret_cast<uint2*>(out)[i] = pack4_f16(v);
+    else reinterpret_cast<float4*>(out)[i] = v;
   }
 }
-extern "C" int mmvid_upsample2x(const float* in, float* out, int N, int H, int W, int C, mmvid_stream_t stream) {
+extern "C" int mmvid_upsample2x(const float* in, void* out, int out_dtype, int N, int H, int W, int C, mmvid_stream_t stream) {
   MMVID_REQUIRE(C % 4 == 0, "C multiple of 4");
+  MMVID_REQUIRE(out_dtype == MMVID_DT_F32 || out_dtype == MMVID_DT_F16, "fp32 or fp16 output");
   const long long total = (long long)N * 4 * H * W * (C / 4);
   const int blocks = (int)std::min<long long>(ceil_div<long long>(total, 256), 148 * 16);
-  upsample2x_kernel<<<blocks, 256, 0, to_stream(stream)>>>((const float4*)in, (float4*)out, H, W, C / 4, total);
+  if (out_dtype == MMVID_DT_F16)
+    upsample2x_kernel<true><<<blocks, 256, 0, to_stream(stream)>>>((const float4*)in, out, H, W, C / 4, total);
+  else
+    upsample2x_kernel<false><<<blocks, 256, 0, to_stream(stream)>>>((const float4*)in, out, H, W, C / 4, total);
   return check_launch("upsample2x");
 }
 
@@ -438,8 +453,9 @@ __global__ void groupnorm_apply_kernel(const float4* __restrict__ in, float4* __
 // no 64-bit division in the loop; four pixels are in flight per thread.  ncu had the generic kernel above at 2.8 TB/s
 // (instruction bound: 64-bit div / mod, per-element statistic loads, accurate expf + IEEE division).
 // swish: 0 none, 1 x * sigmoid(x) with expf and IEEE division (fp32 parity mode), 2 MUFU ex2 + rcp (~1e-6 relative).
-template <int SWISH>
-__global__ void __launch_bounds__(256) groupnorm_apply2_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+// OUT16: the result feeds a kind::f16 implicit-GEMM conv and is written as fp16 (half the store bytes).
+template <int SWISH, bool OUT16>
+__global__ void __launch_bounds__(256) groupnorm_apply2_kernel(const float4* __restrict__ in, void* __restrict__ out,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ stats, int HW, int C, int G) {
   const int C4 = C >> 2, cpg = C / G;
@@ -466,7 +482,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply2_kernel(const float4* __r
     return make_float4(r[0], r[1], r[2], r[3]);
   };
   const float4* src = in + (long long)n * HW * C4 + c4;
-  float4* dst = out + (long long)n * HW * C4 + c4;
+  const long long obase = (long long)n * HW * C4 + c4;
+  auto put = [&](long long pix, float4 v) {
+    if (OUT16) reinterpret_cast<uint2*>(out)[obase + pix * C4] = pack4_f16(v);
+    else reinterpret_cast<float4*>(out)[obase + pix * C4] = v;
+  };
   const int step = gridDim.x * ppb;
   int p = blockIdx.x * ppb + prow;
   for (; p + 3 * step < HW; p += 4 * step) {
@@ -474,9 +494,9 @@ __global__ void __launch_bounds__(256) groupnorm_apply2_kernel(const float4* __r
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = src[(long long)(p + u * step) * C4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) dst[(long long)(p + u * step) * C4] = f(v[u]);
+    for (int u = 0; u < 4; ++u) put(p + u * step, f(v[u]));
   }
-  for (; p < HW; p += step) dst[(long long)p * C4] = f(src[(long long)p * C4]);
+  for (; p < HW; p += step) put(p, f(src[(long long)p * C4]));
 }
 
 static int groupnorm_stats_launch(const float* in, float* stats, int N, int HW, int C, int groups, float eps,
@@ -503,9 +523,11 @@ extern "C" int mmvid_groupnorm_stats(const float* in, float* stats, int N, int H
   return groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, to_stream(stream));
 }
 
-extern "C" int mmvid_groupnorm(const float* in, float* out, const float* gamma, const float* beta, float* stats,
-                               int N, int HW, int C, int groups, float eps, int swish, mmvid_stream_t stream) {
+extern "C" int mmvid_groupnorm(const float* in, void* out, int out_dtype, const float* gamma, const float* beta,
+                               float* stats, int N, int HW, int C, int groups, float eps, int swish,
+                               mmvid_stream_t stream) {
   MMVID_REQUIRE(C % groups == 0 && C % 4 == 0 && C <= 1024, "C divisible by groups and 4, <= 1024");
+  MMVID_REQUIRE(out_dtype == MMVID_DT_F32 || out_dtype == MMVID_DT_F16, "fp32 or fp16 output");
   if (N == 0) return MMVID_OK;
   cudaStream_t st = to_stream(stream);
   int rc = groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, st);
@@ -516,12 +538,18 @@ extern "C" int mmvid_groupnorm(const float* in, float* out, const float* gamma, 
     int gx = std::max(1, std::min(ceil_div(HW, ppb * 4), ceil_div(148 * 8, N)));
     dim3 grid(gx, N);
     const float4* i4 = (const float4*)in;
-    float4* o4 = (float4*)out;
-    if (swish == 0) groupnorm_apply2_kernel<0><<<grid, 256, 0, st>>>(i4, o4, gamma, beta, stats, HW, C, groups);
-    else if (swish == 2) groupnorm_apply2_kernel<2><<<grid, 256, 0, st>>>(i4, o4, gamma, beta, stats, HW, C, groups);
-    else groupnorm_apply2_kernel<1><<<grid, 256, 0, st>>>(i4, o4, gamma, beta, stats, HW, C, groups);
+    if (out_dtype == MMVID_DT_F16) {
+      if (swish == 0) groupnorm_apply2_kernel<0, true><<<grid, 256, 0, st>>>(i4, out, gamma, beta, stats, HW, C, groups);
+      else if (swish == 2) groupnorm_apply2_kernel<2, true><<<grid, 256, 0, st>>>(i4, out, gamma, beta, stats, HW, C, groups);
+      else groupnorm_apply2_kernel<1, true><<<grid, 256, 0, st>>>(i4, out, gamma, beta, stats, HW, C, groups);
+    } else {
+      if (swish == 0) groupnorm_apply2_kernel<0, false><<<grid, 256, 0, st>>>(i4, out, gamma, beta, stats, HW, C, groups);
+      else if (swish == 2) groupnorm_apply2_kernel<2, false><<<grid, 256, 0, st>>>(i4, out, gamma, beta, stats, HW, C, groups);
+      else groupnorm_apply2_kernel<1, false><<<grid, 256, 0, st>>>(i4, out, gamma, beta, stats, HW, C, groups);
+    }
     return check_launch("groupnorm_apply2");
   }
+  MMVID_REQUIRE(out_dtype == MMVID_DT_F32, "fp16 GroupNorm output needs C / 4 to divide 256");
   const long long total4 = (long long)N * HW * (C / 4);
   const int blocks = (int)std::min<long long>(ceil_div<long long>(total4, 256), 148 * 16);
   groupnorm_apply_kernel<<<blocks, 256, 0, st>>>((const float4*)in, (float4*)out, gamma, beta, stats, HW, C, groups,

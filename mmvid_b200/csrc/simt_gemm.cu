@@ -258,7 +258,7 @@ extern "C" int mmvid_conv2d(const mmvid_conv_params* p, mmvid_stream_t stream) {
   MMVID_REQUIRE(!(p->out_nchw && p->residual), "residual unsupported with NCHW output");
   if (p->precision != MMVID_FP32) return mmvid_conv2d_tc(p, to_stream(stream));
   GemmArgs g{};
-  g.A = p->in; g.B = p->w; g.ldb_n = (long long)p->KH * p->KW * p->Cin; g.ldb_k = 1;
+  g.A = static_cast<const float*>(p->in); g.B = static_cast<const float*>(p->w); g.ldb_n = (long long)p->KH * p->KW * p->Cin; g.ldb_k = 1;
   g.C = p->out; g.ldc = p->Cout; g.bias = p->bias; g.residual = p->residual; g.ldr = p->Cout;
   g.M = (long long)p->N * p->Ho * p->Wo; g.N = p->Cout; g.K = p->KH * p->KW * p->Cin;
   g.batch2 = 1; g.alpha = 1.f; g.act = MMVID_ACT_NONE;

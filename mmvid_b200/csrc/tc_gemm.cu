@@ -801,17 +801,19 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
 // ------------------------------------------------------------------------------------------------
 extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
-  MMVID_REQUIRE(p->precision == MMVID_TF32, "tensor-core conv runs kind::tf32");
+  MMVID_REQUIRE(p->precision == MMVID_TF32 || p->precision == MMVID_F16, "tensor-core conv runs kind::tf32 or kind::f16 (fp16)");
+  const bool f16 = p->precision == MMVID_F16;
+  const int esz = f16 ? 2 : 4, BKE = f16 ? 64 : 32, dt = f16 ? MMVID_DT_F16 : MMVID_DT_F32;
   MMVID_REQUIRE(p->stride == 1 && !p->in_nchw && !p->out_nchw && !p->pre_affine && !p->post_clamp && !p->upsample,
                 "tc conv: stride 1, NHWC, no fused resampling");
-  MMVID_REQUIRE(p->Cin % 32 == 0 && p->Cout % 4 == 0, "tc conv: Cin % 32 == 0, Cout % 4 == 0");
+  MMVID_REQUIRE(p->Cin % BKE == 0 && p->Cout % 4 == 0, "tc conv: Cin % 32 == 0 (fp16: 64), Cout % 4 == 0");
   MMVID_REQUIRE(pow2(p->H) && pow2(p->W) && p->Ho == p->H && p->Wo == p->W, "tc conv: power-of-two 'same' convolution");
   const long long M = (long long)p->N * p->H * p->W;
   const int K = p->KH * p->KW * p->Cin;
-  // EXPERIMENTAL (MMVID_CONV_SWAP=1, not validated on hardware yet): transposed tile for the Cout = 128 layers - A = 128
-  // output channels of the packed weights, B = 256 pixels - so that the MMA is 256 wide and leaves the ~100 clk SS floor
+  // Transposed tile for the layers with Cout = 128 (MMVID_CONV_SWAP, tf32 only): A = 128 output channels of the packed
+  // weights, B = 256 pixels, so that the MMA is 256 wide and leaves the ~100 clk SS floor
   // (profiles/r1_g_gemm_pipeline.md); the result chunk is transposed in shared memory before the bulk store.
-  if (env_int("MMVID_CONV_SWAP", 0) && p->Cout % 128 == 0 && M % 256 == 0) {
+  if (!f16 && env_int("MMVID_CONV_SWAP", 0) && p->Cout % 128 == 0 && M % 256 == 0) {
     const int BW2 = p->W < 256 ? p->W : 256;
     const int BH2 = (256 / BW2) < p->H ? (256 / BW2) : p->H;
     const int BNI2 = 256 / (BW2 * BH2);
@@ -845,25 +847,25 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
-    uint64_t str[3] = {(uint64_t)p->Cin * 4, (uint64_t)p->W * p->Cin * 4, (uint64_t)p->H * p->W * p->Cin * 4};
-    uint32_t box[4] = {32, (uint32_t)BW, (uint32_t)BH, (uint32_t)BNI};
-    int rc = make_tensor_map(&tmA, p->in, MMVID_DT_F32, 4, dims, str, box);
+    uint64_t str[3] = {(uint64_t)p->Cin * esz, (uint64_t)p->W * p->Cin * esz, (uint64_t)p->H * p->W * p->Cin * esz};
+    uint32_t box[4] = {(uint32_t)BKE, (uint32_t)BW, (uint32_t)BH, (uint32_t)BNI};
+    int rc = make_tensor_map(&tmA, p->in, dt, 4, dims, str, box);
     if (rc) return rc;
   }
   const int BN = pick_bn(M, p->Cout);
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)p->Cout};
-    uint64_t str[1] = {(uint64_t)K * 4};
-    uint32_t box[2] = {32, (uint32_t)BN};
-    int rc = make_tensor_map(&tmB, p->w, MMVID_DT_F32, 2, dims, str, box);
+    uint64_t str[1] = {(uint64_t)K * esz};
+    uint32_t box[2] = {(uint32_t)BKE, (uint32_t)BN};
+    int rc = make_tensor_map(&tmB, p->w, dt, 2, dims, str, box);
     if (rc) return rc;
   }
   EpiArgs e{};
-  e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_h16 = 0; e.op_f16 = 0;
+  e.bias = p->bias; e.residual = p->residual; e.ldr = p->Cout; e.C = p->out; e.ldc = p->Cout; e.c_h16 = 0; e.op_f16 = f16;
   e.M = M; e.N = p->Cout; e.K = K; e.act = MMVID_ACT_NONE;
   e.cCin = p->Cin; e.cKW = p->KW; e.cPadT = p->pad_t; e.cPadL = p->pad_l; e.cBW = BW; e.cBH = BH; e.cBNI = BNI;
   e.cW = p->W; e.cH = p->H;
-  return launch_bn<true, true>(BN, tmA, tmB, e, st);
+  return f16 ? launch_bn<false, true>(BN, tmA, tmB, e, st) : launch_bn<true, true>(BN, tmA, tmB, e, st);
 }
 
 

@@ -116,16 +116,18 @@ def layernorm(x, weight, bias, eps=1e-5, out_dtype=torch.float32):
     return out.view(*x.shape[:-1], D)
 
 
-def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None, fast=False):
-    """x: float32 [N, H, W, C] contiguous.  fast: swish through MUFU ex2 / rcp (tensor-core precision modes)."""
+def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None, fast=False, out_dtype=torch.float32):
+    """x: float32 [N, H, W, C] contiguous.  fast: swish through MUFU ex2 / rcp (tensor-core precision modes).
+    out_dtype=torch.float16: the result feeds a kind::f16 conv (not in place)."""
     lib = L.load()
     _req(x_nhwc, torch.float32, "x")
     assert x_nhwc.is_contiguous()
     N, H, W, Cc = x_nhwc.shape
-    out = torch.empty_like(x_nhwc) if out is None else out
+    if out is None or out.dtype != out_dtype:
+        out = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=out_dtype)
     stats = torch.empty(int(lib.mmvid_groupnorm_scratch_floats(N, groups)), device=x_nhwc.device, dtype=torch.float32)
-    L.check(lib.mmvid_groupnorm(_ptr(x_nhwc), _ptr(out), _ptr(weight), _ptr(bias), _ptr(stats), N, H * W, Cc, groups,
-                                eps, (2 if fast else 1) if swish else 0, _stream()), "groupnorm")
+    L.check(lib.mmvid_groupnorm(_ptr(x_nhwc), _ptr(out), _dt(out), _ptr(weight), _ptr(bias), _ptr(stats), N, H * W, Cc,
+                                groups, eps, (2 if fast else 1) if swish else 0, _stream()), "groupnorm")
     return out
 
 
@@ -307,9 +309,14 @@ def codebook_gather(ids, codebook):
 
 def conv2d(x, w_packed, bias, *, stride=1, pad=(1, 1), out_hw=None, upsample=False, residual=None, in_nchw=False,
            out_nchw=False, pre_affine=False, post_clamp=False, precision=FP32):
-    """x: float32 NHWC [N,H,W,Cin] (or NCHW if in_nchw); w_packed [Cout,KH,KW,Cin]; returns NHWC (or NCHW)."""
+    """x: float32 NHWC [N,H,W,Cin] (or NCHW if in_nchw); w_packed [Cout,KH,KW,Cin]; returns float32 NHWC (or NCHW).
+    precision 'fp16': x and w_packed are float16 (kind::f16 implicit GEMM, fp32 accumulate / bias / residual / output)."""
     lib = L.load()
-    _req(x, torch.float32)
+    if precision_id(precision) == F16:
+        _req(x, torch.float16)
+        _req(w_packed, torch.float16, "w_packed")
+    else:
+        _req(x, torch.float32)
     assert x.is_contiguous() and w_packed.is_contiguous()
     if in_nchw:
         N, Cin, H, W = x.shape
@@ -337,12 +344,13 @@ def conv2d(x, w_packed, bias, *, stride=1, pad=(1, 1), out_hw=None, upsample=Fal
     return out
 
 
-def upsample2x(x):
-    """nearest x2 on NHWC float32 (model.py:57-59)."""
+def upsample2x(x, out_dtype=torch.float32):
+    """nearest x2 on NHWC float32 (model.py:57-59); out_dtype=torch.float16 when a kind::f16 conv consumes it."""
     lib = L.load()
+    _req(x, torch.float32)
     N, H, W, Cc = x.shape
-    out = torch.empty(N, 2 * H, 2 * W, Cc, device=x.device, dtype=torch.float32)
-    L.check(lib.mmvid_upsample2x(_ptr(x), _ptr(out), N, H, W, Cc, _stream()), "upsample2x")
+    out = torch.empty(N, 2 * H, 2 * W, Cc, device=x.device, dtype=out_dtype)
+    L.check(lib.mmvid_upsample2x(_ptr(x), _ptr(out), _dt(out), N, H, W, Cc, _stream()), "upsample2x")
     return out
 
 

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
-from ._lib import FP32, MASK_NONE, PRECISIONS, TF32
+from ._lib import F16, FP32, MASK_NONE, PRECISIONS, TF32
 
 # mmvid_pytorch/data/vqgan.1024.config.yml:5-21 (the only VQGAN configuration MMVID ships)
 VQGAN_1024_CONFIG = dict(
@@ -150,12 +150,16 @@ class _PackCache:
     def __init__(self):
         self._d = {}
 
-    def conv(self, p):
+    def conv(self, p, dtype=torch.float32):
         tag = (p.data_ptr(), p._version, _lib.weights_epoch())
-        hit = self._d.get(id(p))
+        key = (id(p), dtype)
+        hit = self._d.get(key)
         if hit is None or hit[0] != tag:
-            hit = (tag, p.detach().permute(0, 2, 3, 1).contiguous())
-            self._d[id(p)] = hit
+            w = p.detach().permute(0, 2, 3, 1)
+            if dtype == torch.float16:
+                w = w.clamp(-65504.0, 65504.0)
+            hit = (tag, w.to(dtype).contiguous())
+            self._d[key] = hit
         return hit[1]
 
     def cat(self, key, params):
@@ -190,17 +194,30 @@ class VQGanVAE1024(nn.Module):
         return PRECISIONS[self.precision] if isinstance(self.precision, str) else self.precision
 
     def _conv3(self, x, conv, **kw):
-        """3x3 conv.  precision 'tf32': stride-1 NHWC convs with Cin % 32 == 0 run on tcgen05 through 4-D TMA
+        """3x3 conv.  precision 'tf32' / 'fp16': stride-1 NHWC convs with Cin % 32 == 0 run on tcgen05 through 4-D TMA
         tiles (nearest-x2 upsampling is materialised first); the 3-channel input/output convs and the stride-2
-        downsample stay on the fp32 implicit-GEMM path."""
+        downsample stay on the fp32 implicit-GEMM path.  'fp16' (decoder): a float16 `x` (written by the GroupNorm /
+        upsample kernel that precedes the conv) selects the kind::f16 implicit GEMM with fp16 packed weights."""
+        if x.dtype == torch.float16:
+            w = self._pack.conv(conv.weight, torch.float16)
+            assert kw.get("stride", 1) == 1 and not kw.get("upsample") and w.shape[3] % 64 == 0
+            return ops.conv2d(x, w, conv.bias, precision=F16, **kw)
         w = self._pack.conv(conv.weight)
         tc_ok = (self._prec() != FP32 and kw.get("stride", 1) == 1 and not kw.get("in_nchw") and not kw.get("out_nchw")
                  and w.shape[3] % 32 == 0 and w.shape[0] % 4 == 0)
         if tc_ok:
             if kw.pop("upsample", False):
-                x = ops.upsample2x(x)
+                x = ops.upsample2x(x, out_dtype=self._act16())
+                if x.dtype == torch.float16:
+                    return ops.conv2d(x, self._pack.conv(conv.weight, torch.float16), conv.bias, precision=F16, **kw)
             return ops.conv2d(x, w, conv.bias, precision=TF32, **kw)
         return ops.conv2d(x, w, conv.bias, precision=FP32, **kw)
+
+    def _act16(self):
+        """dtype the GroupNorm / upsample kernels hand to the 3x3 convs: float16 in the decoder of an 'fp16' VQGAN (same
+        10-bit mantissa as the tf32 path at twice the MMA rate and half the bytes), float32 otherwise.  The encoder always
+        stays on the fp32 / tf32 kernels: its VQ indices must not depend on the throughput mode."""
+        return torch.float16 if (self._prec() == F16 and getattr(self, "_decoding", False)) else torch.float32
 
     def _conv1(self, x, conv, residual=None):
         N, H, W, C = x.shape
@@ -211,13 +228,14 @@ class VQGanVAE1024(nn.Module):
 
     def _lin_prec(self):
         p = self._prec()
-        return FP32 if p == FP32 else TF32  # bf16 is not used inside the VQGAN: 1x1 convs run TF32 at most
+        return FP32 if p == FP32 else TF32  # 1x1 convs / spatial attention projections run TF32 at most
 
     def _resblock(self, x, blk):
         fast = self._prec() != FP32  # tensor-core modes: MUFU sigmoid; fp32 parity mode keeps expf + IEEE division
-        t = ops.groupnorm(x, blk.norm1.weight, blk.norm1.bias, swish=True, fast=fast)
+        a16 = self._act16()
+        t = ops.groupnorm(x, blk.norm1.weight, blk.norm1.bias, swish=True, fast=fast, out_dtype=a16)
         t = self._conv3(t, blk.conv1)
-        t = ops.groupnorm(t, blk.norm2.weight, blk.norm2.bias, swish=True, out=t, fast=fast)
+        t = ops.groupnorm(t, blk.norm2.weight, blk.norm2.bias, swish=True, out=t, fast=fast, out_dtype=a16)
         sc = x if blk.in_channels == blk.out_channels else self._conv1(x, blk.nin_shortcut)
         return self._conv3(t, blk.conv2, residual=sc)
 
@@ -273,6 +291,13 @@ class VQGanVAE1024(nn.Module):
     @torch.no_grad()
     def _decode_latent(self, z):
         """z: float32 NHWC [N, h, w, 256] codebook vectors -> float [N,3,H,W] in [0,1]."""
+        self._decoding = True
+        try:
+            return self._decode_latent_impl(z)
+        finally:
+            self._decoding = False
+
+    def _decode_latent_impl(self, z):
         dec = self.model.decoder
         h = self._conv1(z, self.model.post_quant_conv)
         h = self._conv3(h, dec.conv_in)

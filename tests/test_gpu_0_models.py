@@ -78,6 +78,27 @@ def test_vae_decode_tf32_tensor_core_pixels(name):
     assert e < 1e-3
 
 
+@pytest.mark.parametrize("name", ["vae_64", "vae_128"])
+def test_vae_decode_fp16_tensor_core_pixels_and_encoder_untouched(name):
+    """precision='fp16': the decoder's 3x3 convs run kind::f16 on fp16 activations; pixels within 1e-3 of the reference's
+    fp32 output.  The ENCODER of the same module stays on the tf32 kernels (its indices must not depend on the decoder's
+    throughput mode): the mismatch rate of its indices against the reference's is reported, next to the tf32 module's."""
+    cfg = VAE_CASES[name]
+    fx = load_fixture(name)
+    vae, _ = build_vae(cfg["image_size"], cfg["seed"], precision="fp16")
+    dec = vae.decode(fx["indices"].cuda())
+    e = relerr(dec, fx["decoded"])
+    img = synth.synth_frames(cfg["batch"], 1, cfg["image_size"], cfg["seed"])[:, 0].cuda()
+    idx16 = vae.get_codebook_indices(img).cpu()
+    vae32, _ = build_vae(cfg["image_size"], cfg["seed"], precision="tf32")
+    idx32 = vae32.get_codebook_indices(img).cpu()
+    mm16, mm32 = int((idx16 != fx["indices"]).sum()), int((idx32 != fx["indices"]).sum())
+    print(f"{name}: fp16 decode relerr {e:.2e}; encoder index mismatches vs reference: {mm16}/{idx16.numel()} (fp16 module), "
+          f"{mm32}/{idx32.numel()} (tf32 module) - bit-exact indices are the fp32 module's contract")
+    assert e < 1e-3
+    assert torch.equal(idx16, idx32)
+
+
 # ------------------------------------------------------------------------------------------------ BERT
 _BERT_CACHE = {}
 

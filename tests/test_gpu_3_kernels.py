@@ -328,6 +328,40 @@ def test_conv3x3_tensor_core_tf32(N, Cin, Cout, H):
     assert relerr(out, ref + res) < 1e-3
 
 
+@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 128, 128, 32), (3, 512, 512, 4), (1, 256, 128, 128), (5, 256, 512, 8),
+                                          (2, 512, 256, 16), (1, 128, 128, 256)])
+def test_conv3x3_tensor_core_fp16_with_fp16_groupnorm_and_upsample_producers(N, Cin, Cout, H):
+    """kind::f16 implicit-GEMM conv (fp16 NHWC activations through {64 ch, BW, BH, N} TMA boxes, fp16 packed weights, fp32
+    accumulate / bias / residual / output) fed by the GroupNorm+swish and nearest-x2 kernels' fp16 outputs: each stage
+    against fp64 at the tf32 tolerance (fp16 carries the same 10-bit mantissa)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 1000 + Cin + H)
+    x = torch.randn(N, Cin, H, H, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, H, H, Cout, generator=g).cuda()
+    gw, gb = torch.randn(Cin, generator=g).cuda(), torch.randn(Cin, generator=g).cuda()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    w16 = _pack(w).half()
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
+    out = ops.conv2d(xn.half(), w16, b, precision="fp16")
+    assert out.dtype == torch.float32 and relerr(out, ref) < 1e-3
+    assert relerr(ops.conv2d(xn.half(), w16, b, residual=res, precision="fp16"), ref + res) < 1e-3
+    # GroupNorm + swish -> fp16 -> conv
+    gn = F.group_norm(x.double(), 32, gw.double(), gb.double(), 1e-6)
+    gn = gn * torch.sigmoid(gn)
+    t16 = ops.groupnorm(xn, gw, gb, swish=True, fast=True, out_dtype=torch.float16)
+    assert t16.dtype == torch.float16 and relerr(t16.float(), gn.permute(0, 2, 3, 1).float()) < 6e-4
+    ref2 = F.conv2d(gn, w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
+    assert relerr(ops.conv2d(t16, w16, b, precision="fp16"), ref2) < 1e-3
+    if H <= 64:  # nearest x2 -> fp16 -> conv (Upsample, model.py:56-62)
+        u16 = ops.upsample2x(xn, out_dtype=torch.float16)
+        up = F.interpolate(x.double(), scale_factor=2.0, mode="nearest")
+        assert u16.shape == (N, 2 * H, 2 * H, Cin) and relerr(u16.float(), up.permute(0, 2, 3, 1).float()) < 6e-4
+        ref3 = F.conv2d(up, w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
+        assert relerr(ops.conv2d(u16, w16, b, precision="fp16"), ref3) < 1e-3
+
+
 def test_upsample2x():
     ops = _ops()
     x = torch.randn(2, 5, 7, 8).cuda()
