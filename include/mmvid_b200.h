@@ -170,7 +170,8 @@ typedef struct {
 long long mmvid_artv_decode_stream_workspace_floats(int B, int D, int H);
 int mmvid_artv_decode_stream(const mmvid_decode_layer16* host_layers, int n_layers, float* h, float* ws,
                              const float* head_ln_w, const float* head_ln_b, const void* head_w16, const float* head_b,
-                             float* logits, int n_logits, int B, int D, int H, int S_max, int pos, int f16,
+                             float* logits, int n_logits, int B, int D, int H, int S_max, int pos,
+                             const int* pos_dev /* optional device step counter added to pos (graph replay) */, int f16,
                              mmvid_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -266,6 +267,10 @@ int mmvid_transpose2d(const float* in, float* out, int R, int C, mmvid_stream_t 
 /* Profiling hook (not part of the data path): CTA (0,0) of every following mmvid_attention launch writes clock64()
  * stamps of its pipeline events into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/att_trace.py. */
 int mmvid_debug_attention_trace(unsigned long long* dev_buf);
+
+/* Profiling hook: CTA 0 of every following mmvid_artv_decode_stream launch writes %globaltimer (ns) stamps of its phase
+ * events into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/decode_trace.py. */
+int mmvid_debug_decode_trace(unsigned long long* dev_buf);
 
 /* Profiling hook: CTA 0 of every following single-CTA tensor-core GEMM (mmvid_linear in TF32 / BF16 precision) writes
  * clock64() stamps of its first 8 tiles into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/gemm_trace.py. */

@@ -81,7 +81,7 @@ SIGNATURES = {
     "mmvid_artv_decode_persistent": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mmvid_artv_decode_fused": (_i, [C.POINTER(DecodeLayer), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mmvid_artv_decode_stream_workspace_floats": (_ll, [_i, _i, _i]),
-    "mmvid_artv_decode_stream": (_i, [C.POINTER(DecodeLayer16), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mmvid_artv_decode_stream": (_i, [C.POINTER(DecodeLayer16), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "mmvid_vq_argmin": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),
@@ -102,6 +102,7 @@ SIGNATURES = {
     "mmvid_embed_backward": (_i, [_p, _i, _i, _i, C.POINTER(EmbedSegment), _p, _p, _p, _p]),
     "mmvid_transpose2d": (_i, [_p, _p, _i, _i, _p]),
     "mmvid_debug_attention_trace": (_i, [_p]),
+    "mmvid_debug_decode_trace": (_i, [_p]),
     "mmvid_debug_mma_rate": (_i, [_i, _i, _p, _p]),
     "mmvid_debug_gemm_trace": (_i, [_p]),
     "mmvid_debug_pick_tile": (_i, [_ll, _i, _i, _i, _i]),

@@ -55,9 +55,18 @@ struct StreamParams {
   float* logits;     // [B, n_logits]
   int n_logits;
   int B, D, H, S_max, pos, Z;
+  const int* pos_dev;  // optional: device-resident step counter added to pos (CUDA-graph replay: same launch, next token)
   int f16;           // 16-bit flavour of weights / cache: 1 = fp16, 0 = bf16
   int slot_bytes;
+  unsigned long long* trace;  // debug timeline (mmvid_debug_decode_trace): globaltimer stamps of CTA 0, normally null
 };
+
+// CTA 0, thread 0 stamps %globaltimer (ns) at phase events when a trace buffer is installed (scripts/decode_trace.py):
+// entry i = phase_index * 8 + {0 phase start, 1 activations staged, 2 LayerNorm done, 3 slab landed, 4 items done,
+// 5 results stored, 6 barrier passed}
+__device__ __forceinline__ void ds_stamp(const StreamParams& p, int phase, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && phase < 64) p.trace[phase * 8 + ev] = globaltimer_ns();
+}
 
 __device__ __forceinline__ float h16_to_f32(uint32_t bits16, int f16) {
   if (f16) return __half2float(__ushort_as_half((unsigned short)bits16));
@@ -80,29 +89,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
                : "memory");
 }
 
-// Sense-reversing grid barrier (all CTAs are co-resident: cooperative launch).  Release: every thread's global writes are
-// ordered before its CTA's arrival by __syncthreads + the arriving thread's fence; acquire: the spinning thread's
-// ld.acquire + fence, then __syncthreads.  The last arriver resets the count before it publishes the new generation.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar) {
+// Grid barrier (all CTAs are co-resident: one per SM).  ONE monotonic counter per launch: the k-th barrier is passed when
+// the counter reaches k * gridDim.x; per CTA one release-add and an acquire spin.  Every thread's global writes are ordered
+// before its CTA's arrival by __syncthreads + the arriving thread's release; the spinning thread's acquire + the closing
+// __syncthreads order the other CTAs' writes before this CTA's reads.  The kernel's exit path resets the counter.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int k) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned int gen;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-    __threadfence();
-    const unsigned int prev = atomicAdd(bar, 1u);
-    if (prev == gridDim.x - 1) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
-    } else {
-      unsigned int g2;
+    const unsigned int target = k * gridDim.x;
+    unsigned int v;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(bar) : "memory");
+    if (v + 1 < target) {
       const uint64_t t0 = globaltimer_ns();
       do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 1) : "memory");
-        if (g2 == gen && globaltimer_ns() - t0 > MBAR_TIMEOUT_NS) asm volatile("trap;");
-      } while (g2 == gen);
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        if (v < target && globaltimer_ns() - t0 > MBAR_TIMEOUT_NS) asm volatile("trap;");
+      } while (v < target);
+    } else {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -156,15 +161,17 @@ __device__ __forceinline__ void issue_slab(const StreamParams& p, int w, int n_w
 template <int MAXB>
 __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const float* __restrict__ A, long long lda, int K,
                            const float* ln_g, const float* ln_b, int N, const float* __restrict__ bias, int act,
-                           const float* residual, float* out, long long ldo, bool qkv_mode, const StreamLayer* L,
-                           float* sm_act, float* sm_part) {
+                           const float* residual, float* out, long long ldo, bool qkv_mode, const StreamLayer* L, int pos,
+                           float* sm_act, float* sm_part, int tphase, const uint64_t* slab_bar, uint32_t slab_par) {
   const int B = p.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ds_stamp(p, tphase, 0);
   // ---- stage A [B, K] (fp32, written by other CTAs before the barrier: L2 loads)
   for (int i = threadIdx.x; i < B * (K >> 2); i += DS_THREADS) {
     const int b = i / (K >> 2), k4 = i - b * (K >> 2);
     reinterpret_cast<float4*>(sm_act)[i] = ldcg_f4(A + b * lda + k4 * 4);
   }
   __syncthreads();
+  ds_stamp(p, tphase, 1);
   if (ln_g != nullptr) {  // clip_model.py:188-193, eps 1e-5; two-pass statistics, one warp per row
     for (int b = warp; b < B; b += DS_WARPS) {
       float* x = sm_act + b * K;
@@ -178,6 +185,9 @@ __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const flo
     }
     __syncthreads();
   }
+  ds_stamp(p, tphase, 2);
+  mbar_wait(const_cast<uint64_t*>(slab_bar), slab_par);  // this phase's weight slab has landed in the ring
+  ds_stamp(p, tphase, 3);
   int lo, hi;
   col_range(N, lo, hi);
   const int C = hi - lo;
@@ -215,6 +225,7 @@ __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const flo
     }
   }
   __syncthreads();
+  ds_stamp(p, tphase, 4);
   for (int i = threadIdx.x; i < C * B; i += DS_THREADS) {
     const int c = i / B, b = i - c * B, n = lo + c;
     float v = 0.f;
@@ -223,7 +234,7 @@ __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const flo
     if (residual) v += __ldcg(residual + b * ldo + n);
     if (qkv_mode && n >= p.D) {  // K / V of the new token straight into the 16-bit caches [B, H, S_max, 64]
       const int cc = n - p.D, which = cc / p.D, c2 = cc - which * p.D, hh = c2 >> 6, d = c2 & 63;
-      uint16_t* dst = (which == 0 ? L->kcache : L->vcache) + (((long long)b * p.H + hh) * p.S_max + p.pos) * 64 + d;
+      uint16_t* dst = (which == 0 ? L->kcache : L->vcache) + (((long long)b * p.H + hh) * p.S_max + pos) * 64 + d;
       *dst = cvt_h16_rt(v, p.f16);
     } else {
       out[b * ldo + n] = v;
@@ -233,8 +244,8 @@ __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const flo
 
 // Single-query attention over the 16-bit cache, split-KV over Z CTAs per (batch, head).  8 lanes x 16 bytes cover one
 // 64-dim row, so a warp load fetches 4 keys; 4 such loads (16 keys) of K and of V are in flight per warp.
-__device__ void attention_phase(const StreamParams& p, const StreamLayer& L, float* sm_red) {
-  const int B = p.B, H = p.H, Z = p.Z, len = p.pos + 1;
+__device__ void attention_phase(const StreamParams& p, const StreamLayer& L, int pos, int Z, float* sm_red) {
+  const int B = p.B, H = p.H, len = pos + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sm_m = sm_red;                 // [16]
   float* sm_l = sm_red + 16;            // [16]
@@ -368,6 +379,11 @@ __device__ void attention_phase(const StreamParams& p, const StreamLayer& L, flo
 
 template <int MAXB>
 __global__ void __launch_bounds__(DS_THREADS, 1) artv_decode_stream_kernel(const __grid_constant__ StreamParams p) {
+  // the step counter of a graph replay lives in device memory
+  const int pos = p.pos + (p.pos_dev != nullptr ? __ldcg(p.pos_dev) : 0);
+  // split-KV factor: at most the host's Z (CTAs per (batch, head)), fewer while the cache is short
+  int Z = p.Z;
+  while (Z > 1 && pos + 1 < Z * 64) --Z;
   extern __shared__ __align__(128) uint8_t sm_raw[];
   __shared__ uint64_t full[DS_SLOTS];
   // carve: ring of DS_SLOTS weight slabs | staged activations [B, 4D] fp32 | partials / attention scratch
@@ -383,53 +399,53 @@ __global__ void __launch_bounds__(DS_THREADS, 1) artv_decode_stream_kernel(const
   }
   __syncthreads();
   const int D = p.D;
-  int w = 0;  // weight phase counter
-  auto next_slab = [&](int wdone) {
-    // slot of phase wdone is free (every warp passed the barrier after reading it): refill it with phase wdone + DS_SLOTS
-    if (threadIdx.x == 0) { fence_proxy_async(); issue_slab(p, wdone + DS_SLOTS, n_wphases, ring, full); }
-  };
-  auto slab_of = [&](int wp) -> const uint8_t* {
-    mbar_wait(&full[wp % DS_SLOTS], (uint32_t)(wp / DS_SLOTS) & 1u);
-    return ring + (size_t)(wp % DS_SLOTS) * p.slot_bytes;
-  };
+  int w = 0;       // weight phase counter (4 per layer + head)
+  int tp = 0;      // phase counter incl. attention (trace index)
+  unsigned int nbar = 0;  // grid barriers passed so far in this launch
   // the ring is primed with phases 0 .. DS_SLOTS-2; phase w + DS_SLOTS - 1 is issued when phase w starts (its slot held
   // phase w - 1, which every warp of this CTA finished before the barrier it has just passed)
+  auto gemv = [&](const float* A, long long lda, int K, const float* ln_g, const float* ln_b, int N, const float* bias, int act,
+                  const float* residual, float* out, long long ldo, bool qkv_mode, const StreamLayer* L) {
+    if (threadIdx.x == 0) { fence_proxy_async(); issue_slab(p, w + DS_SLOTS - 1, n_wphases, ring, full); }
+    gemv_phase<MAXB>(p, ring + (size_t)(w % DS_SLOTS) * p.slot_bytes, A, lda, K, ln_g, ln_b, N, bias, act, residual, out, ldo,
+                     qkv_mode, L, pos, sm_act, sm_part, tp, &full[w % DS_SLOTS], (uint32_t)(w / DS_SLOTS) & 1u);
+    ++w;
+  };
+  auto barrier = [&]() {
+    ds_stamp(p, tp, 5);
+    grid_barrier(p.bar, ++nbar);
+    ds_stamp(p, tp, 6);
+    ++tp;
+  };
   for (int li = 0; li < p.n_layers; ++li) {
     const StreamLayer& L = p.layers[li];
-    // ---- QKV: q -> p.q, k / v -> caches
-    if (threadIdx.x == 0) { fence_proxy_async(); issue_slab(p, w + DS_SLOTS - 1, n_wphases, ring, full); }
-    gemv_phase<MAXB>(p, slab_of(w), p.h, D, D, L.ln1_w, L.ln1_b, 3 * D, L.in_b, MMVID_ACT_NONE, nullptr, p.q, D, true, &L,
-                     sm_act, sm_part);
-    ++w;
-    grid_barrier(p.bar);
-    // ---- attention over the cache (no weights: the ring keeps filling meanwhile)
-    attention_phase(p, L, sm_part);
-    grid_barrier(p.bar);
-    // ---- out-proj + residual
-    if (threadIdx.x == 0) { fence_proxy_async(); issue_slab(p, w + DS_SLOTS - 1, n_wphases, ring, full); }
-    gemv_phase<MAXB>(p, slab_of(w), p.att, D, D, nullptr, nullptr, D, L.out_b, MMVID_ACT_NONE, p.h, p.h, D, false, &L, sm_act,
-                     sm_part);
-    ++w;
-    grid_barrier(p.bar);
-    // ---- LN2 + c_fc + QuickGELU
-    if (threadIdx.x == 0) { fence_proxy_async(); issue_slab(p, w + DS_SLOTS - 1, n_wphases, ring, full); }
-    gemv_phase<MAXB>(p, slab_of(w), p.h, D, D, L.ln2_w, L.ln2_b, 4 * D, L.fc_b, MMVID_ACT_QUICKGELU, nullptr, p.mid, 4 * D,
-                     false, &L, sm_act, sm_part);
-    ++w;
-    grid_barrier(p.bar);
-    // ---- c_proj + residual
-    if (threadIdx.x == 0) { fence_proxy_async(); issue_slab(p, w + DS_SLOTS - 1, n_wphases, ring, full); }
-    gemv_phase<MAXB>(p, slab_of(w), p.mid, 4 * D, 4 * D, nullptr, nullptr, D, L.proj_b, MMVID_ACT_NONE, p.h, p.h, D, false, &L,
-                     sm_act, sm_part);
-    ++w;
-    grid_barrier(p.bar);
+    gemv(p.h, D, D, L.ln1_w, L.ln1_b, 3 * D, L.in_b, MMVID_ACT_NONE, nullptr, p.q, D, true, &L);  // q -> p.q, k / v -> caches
+    barrier();
+    ds_stamp(p, tp, 0);
+    attention_phase(p, L, pos, Z, sm_part);  // no weights: the ring keeps filling meanwhile
+    barrier();
+    gemv(p.att, D, D, nullptr, nullptr, D, L.out_b, MMVID_ACT_NONE, p.h, p.h, D, false, &L);     // out-proj + residual
+    barrier();
+    gemv(p.h, D, D, L.ln2_w, L.ln2_b, 4 * D, L.fc_b, MMVID_ACT_QUICKGELU, nullptr, p.mid, 4 * D, false, &L);
+    barrier();
+    gemv(p.mid, 4 * D, 4 * D, nullptr, nullptr, D, L.proj_b, MMVID_ACT_NONE, p.h, p.h, D, false, &L);  // c_proj + residual
+    barrier();
   }
-  if (p.head_w != nullptr) {
-    gemv_phase<MAXB>(p, slab_of(w), p.h, D, D, p.head_ln_w, p.head_ln_b, p.n_logits, p.head_b, MMVID_ACT_NONE, nullptr,
-                     p.logits, p.n_logits, false, nullptr, sm_act, sm_part);
+  if (p.head_w != nullptr)
+    gemv(p.h, D, D, p.head_ln_w, p.head_ln_b, p.n_logits, p.head_b, MMVID_ACT_NONE, nullptr, p.logits, p.n_logits, false, nullptr);
+  ds_stamp(p, tp, 5);
+  // leave the barrier counter at zero for the next launch: the last CTA to get here resets it (every CTA has passed its
+  // last barrier wait before it arrives here, so nobody reads the counter any more)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(p.bar + 1, 1u) == gridDim.x - 1) {
+      atomicExch(p.bar, 0u);
+      atomicExch(p.bar + 1, 0u);
+    }
   }
-  (void)next_slab;
 }
+
+unsigned long long* g_decode_trace = nullptr;
 
 size_t stream_ws_floats(int B, int D, int H, int Z) {
   // q, att [B, D] | mid [B, 4D] | part [B*H, Z, 66] | counters [B*H] | barrier [2] (+ padding)
@@ -437,6 +453,13 @@ size_t stream_ws_floats(int B, int D, int H, int Z) {
 }
 
 }  // namespace
+
+// Profiling hook: CTA 0 of every following mmvid_artv_decode_stream launch writes %globaltimer stamps of its phase events
+// into dev_buf (>= 512 uint64; NULL switches it off).  Layout: ds_stamp.
+extern "C" int mmvid_debug_decode_trace(unsigned long long* dev_buf) {
+  g_decode_trace = dev_buf;
+  return MMVID_OK;
+}
 
 extern "C" long long mmvid_artv_decode_stream_workspace_floats(int B, int D, int H) {
   return (long long)stream_ws_floats(B, D, H, 16);
@@ -449,7 +472,7 @@ extern "C" long long mmvid_artv_decode_stream_workspace_floats(int B, int D, int
 extern "C" int mmvid_artv_decode_stream(const mmvid_decode_layer16* layers, int n_layers, float* h, float* ws,
                                         const float* head_ln_w, const float* head_ln_b, const void* head_w16,
                                         const float* head_b, float* logits, int n_logits, int B, int D, int H, int S_max,
-                                        int pos, int f16, mmvid_stream_t stream) {
+                                        int pos, const int* pos_dev, int f16, mmvid_stream_t stream) {
   MMVID_REQUIRE(B >= 1 && B <= DS_MAX_B, "1 <= B <= 8");
   MMVID_REQUIRE(n_layers >= 1 && n_layers <= DS_MAX_LAYERS, "1..24 layers");
   MMVID_REQUIRE(D == H * 64 && D % 128 == 0, "D = 64 H, multiple of 128");
@@ -494,12 +517,11 @@ extern "C" int mmvid_artv_decode_stream(const mmvid_decode_layer16* layers, int 
                   "16-byte aligned weights and caches");
   }
   p.n_layers = n_layers;
-  const int len = pos + 1;
   int Z = G / (B * H);
   if (Z < 1) Z = 1;
   if (Z > 16) Z = 16;
-  while (Z > 1 && len < Z * 64) --Z;  // short caches: fewer, fuller splits
-  p.Z = Z;
+  p.Z = Z;  // upper bound; the kernel uses fewer, fuller splits while the cache is short
+  p.pos_dev = pos_dev;
   p.h = h;
   p.q = ws;
   p.att = p.q + (size_t)B * D;
@@ -510,6 +532,7 @@ extern "C" int mmvid_artv_decode_stream(const mmvid_decode_layer16* layers, int 
   p.head_ln_w = head_ln_w; p.head_ln_b = head_ln_b; p.head_b = head_b; p.head_w = (const uint16_t*)head_w16;
   p.logits = logits; p.n_logits = n_logits;
   p.B = B; p.D = D; p.H = H; p.S_max = S_max; p.pos = pos; p.f16 = f16 ? 1 : 0; p.slot_bytes = (int)slot;
+  p.trace = g_decode_trace;
   static size_t smem_set[2] = {0, 0};
   void* kern = maxb == 4 ? (void*)artv_decode_stream_kernel<4> : (void*)artv_decode_stream_kernel<8>;
   if (smem > smem_set[maxb == 8]) {
@@ -517,8 +540,17 @@ extern "C" int mmvid_artv_decode_stream(const mmvid_decode_layer16* layers, int 
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(artv_decode_stream): %s", cudaGetErrorString(err));
     smem_set[maxb == 8] = smem;
   }
+  // Co-residency of the G = #SMs CTAs (1 per SM by shared memory) is what the grid barrier needs.  A cooperative launch
+  // asserts it; under stream capture (the per-token CUDA graph of DALLE.generate_images) a plain launch is used: the
+  // grid still fits the device exactly, and CTAs that wait for an SM held by the predecessor's tail are merely late.
   void* args[] = {&p};
-  cudaError_t err = cudaLaunchCooperativeKernel(kern, dim3(G), dim3(DS_THREADS), args, smem, to_stream(stream));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(to_stream(stream), &cap);
+  cudaError_t err;
+  if (cap == cudaStreamCaptureStatusNone)
+    err = cudaLaunchCooperativeKernel(kern, dim3(G), dim3(DS_THREADS), args, smem, to_stream(stream));
+  else
+    err = cudaLaunchKernel(kern, dim3(G), dim3(DS_THREADS), args, smem, to_stream(stream));
   count_launch();
   if (err != cudaSuccess) return fail(MMVID_ECUDA, "artv_decode_stream launch: %s", cudaGetErrorString(err));
   return MMVID_OK;

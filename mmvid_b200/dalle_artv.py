@@ -336,7 +336,66 @@ class DALLE(nn.Module):
         trace = kwargs.get("logits_trace")  # optional list: receives the [B, 1024] image logits of every step (tests)
         max_new = kwargs.get("max_new")     # stop after this many sampled tokens and return them (parity tests)
         n_steps = self.target_seq_len if max_new is None else min(int(max_new), self.target_seq_len)
-        for t in range(n_steps):
+
+        def stream_step(h_buf, pos, pos_dev=None):
+            rc = lib.mmvid_artv_decode_stream(layers16, len(blocks), ops._ptr(h_buf), ops._ptr(ws16), ops._ptr(ln.weight),
+                                              ops._ptr(ln.bias), ops._ptr(head_w16), ops._ptr(head_b), ops._ptr(logits_buf),
+                                              self.num_image_tokens, B, D, H, S_max, pos, ops._ptr(pos_dev),
+                                              int(h16 == torch.float16), ops._stream())
+            if rc == 1:
+                raise RuntimeError("mmvid_artv_decode_stream: shape does not fit the kernel's shared-memory plan; "
+                                   "use precision='fp32' (decode_impl='fused')")
+            L.check(rc, "artv_decode_stream")
+
+        graphed = (stream and self.sampling_mode != "reference" and trace is None and n_steps > 2
+                   and os.environ.get("MMVID_CUDA_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing())
+        if graphed:
+            # The token loop is a chain of ~8 short launches per token whose host side (Python, ctypes, torch dispatch)
+            # costs several times the device time of the one-launch decode step.  One token step - softmax, multinomial,
+            # token store, embedding + position gather, decode kernel, step counter - is captured ONCE into a CUDA graph; the
+            # step index lives in device memory (t_dev), so every replay is the next token.
+            emb_w = self.image_emb.weight.detach()
+            t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            logits_buf.copy_(logits)
+            saved_logits = logits_buf.clone()
+            h_buf = xt.view(B, D)
+            inv_t = 1.0 / float(temperature)
+
+            def token_step():
+                lg = logits_buf * inv_t if temperature != 1.0 else logits_buf
+                probs = ops.softmax_logits(lg)
+                sample = torch.multinomial(probs, 1)
+                t_idx = t_dev.long()
+                out_tokens.scatter_(1, t_idx.view(1, 1).expand(B, 1), sample)
+                h_buf.copy_(emb_w[sample[:, 0]] + pos_table.index_select(0, t_idx))
+                stream_step(h_buf, P, t_dev)
+                t_dev.add_(1)
+
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up: one-time kernel attributes and allocator state; then restore the inputs
+                token_step()
+                logits_buf.copy_(saved_logits)
+                t_dev.zero_()
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(graph):
+                token_step()
+            per_replay = L.launch_count() - n0
+            logits_buf.copy_(saved_logits)
+            t_dev.zero_()
+            for _ in range(n_steps - 1):
+                graph.replay()
+            L.add_launch_count(per_replay * (n_steps - 2))
+            # the last token only needs the sampling half of the step
+            lg = logits_buf * inv_t if temperature != 1.0 else logits_buf
+            out_tokens[:, n_steps - 1] = torch.multinomial(ops.softmax_logits(lg), 1)[:, 0]
+            n_steps_loop = 0
+        else:
+            n_steps_loop = n_steps
+        for t in range(n_steps_loop):
             if trace is not None:
                 trace.append(logits.clone())
             # top_k keeps >= 1024 entries (k = 25888 at the default 0.5), so only the masked logits (-FLT_MAX -> prob 0)
@@ -357,14 +416,7 @@ class DALLE(nn.Module):
             h = xt.view(B, D)
             pos = P + t
             if stream:
-                rc = lib.mmvid_artv_decode_stream(layers16, len(blocks), ops._ptr(h), ops._ptr(ws16), ops._ptr(ln.weight),
-                                                  ops._ptr(ln.bias), ops._ptr(head_w16), ops._ptr(head_b), ops._ptr(logits_buf),
-                                                  self.num_image_tokens, B, D, H, S_max, pos, int(h16 == torch.float16),
-                                                  ops._stream())
-                if rc == 1:
-                    raise RuntimeError("mmvid_artv_decode_stream: shape does not fit the kernel's shared-memory plan; "
-                                       "set decode_impl='fused' with precision='fp32'")
-                L.check(rc, "artv_decode_stream")
+                stream_step(h, pos)
                 logits = logits_buf
                 continue
             if native and fused:

@@ -44,19 +44,38 @@ def all_gather_variable(x, sizes=None):
     return torch.cat(chunks, 0)
 
 
+def _generate_per_sample(model, text, visual, seeds, gen_kwargs):
+    """One sample at a time, each under its own seed: the result of sample i depends on (prompt i, seed i) only, so any
+    partition of the batch over ranks reproduces the single-process output exactly."""
+    imgs, seqs = [], []
+    for i in range(text.shape[0]):
+        torch.manual_seed(int(seeds[i]))
+        im, _, sq = model.generate_images(text[i:i + 1], visual=None if visual is None else visual[i:i + 1], **gen_kwargs)
+        imgs.append(im)
+        seqs.append(sq)
+    return torch.cat(imgs, 0), [], (torch.cat(seqs, 0) if seqs[0] is not None else None)
+
+
 @torch.no_grad()
-def generate_images_sharded(model, text, visual=None, **gen_kwargs):
+def generate_images_sharded(model, text, visual=None, sample_seeds=None, **gen_kwargs):
     """Global batch in, global batch out.  Rank r generates samples [lo_r, hi_r) with its replica and the decoded
-    frames (and token ids) are all-gathered once at the end.  Per-rank RNG: callers seed `seed + rank`
-    (train.py:87 does the same) in throughput mode."""
+    frames (and token ids) are all-gathered once at the end.  RNG: in throughput mode callers seed `seed + rank`
+    (train.py:87 does the same) and the whole local shard is sampled at once; `sample_seeds` (one int per GLOBAL sample)
+    selects partition-independent sampling instead: sample i is generated alone under seed sample_seeds[i], so the
+    gathered ids / frames equal those of a single process given the same seeds."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
+        if sample_seeds is not None:
+            return _generate_per_sample(model, text, visual, sample_seeds, gen_kwargs)
         return model.generate_images(text, visual=visual, **gen_kwargs)
     rank = dist.get_rank()
     n = text.shape[0]
     sizes = [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
     t_loc, v_loc = shard_batch(text, rank, world), shard_batch(visual, rank, world)
-    if t_loc.shape[0] > 0:
+    if t_loc.shape[0] > 0 and sample_seeds is not None:
+        lo, hi = shard_bounds(n, rank, world)
+        images, extra, seq = _generate_per_sample(model, t_loc, v_loc, list(sample_seeds)[lo:hi], gen_kwargs)
+    elif t_loc.shape[0] > 0:
         images, extra, seq = model.generate_images(t_loc, visual=v_loc, **gen_kwargs)
     else:
         raise RuntimeError("global batch smaller than world size")

@@ -1,7 +1,7 @@
 """Times one ART-V decode step (persistent cooperative kernel vs native per-layer launches) at fixed cache lengths."""
 import argparse, sys, ctypes as C, torch
 ap = argparse.ArgumentParser()
-ap.add_argument("--impl", default="fused,persistent,native")
+ap.add_argument("--impl", default="stream,fused,persistent,native")
 ap.add_argument("--pos", default="400,1300,2300")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--warm", type=int, default=3)
@@ -22,7 +22,20 @@ for li in range(NL):
     keep.append(t)
     for k, v in t.items(): setattr(layers[li], k, v.data_ptr())
 ws = torch.zeros(int(lib.mmvid_artv_decode_workspace_floats(B, D, H)), device=dev)
+# 16-bit copies for the streaming kernel (decode_stream.cu)
+layers16 = (L.DecodeLayer16 * NL)()
+keep16 = []
+for li in range(NL):
+    t = keep[li]
+    t16 = {k: t[k].half() for k in ("in_w", "out_w", "fc_w", "proj_w", "kcache", "vcache")}
+    keep16.append(t16)
+    for k in ("ln1_w", "ln1_b", "in_b", "out_b", "ln2_w", "ln2_b", "fc_b", "proj_b"):
+        setattr(layers16[li], k, t[k].data_ptr())
+    for k, v in t16.items():
+        setattr(layers16[li], k, v.data_ptr())
+ws16 = torch.zeros(int(lib.mmvid_artv_decode_stream_workspace_floats(B, D, H)), device=dev)
 head_w, head_b = r(1024, D), r(1024)
+head_w16 = head_w.half()
 lnw, lnb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
 logits = torch.empty(B, 1024, device=dev)
 h0 = r(B, D) * 50
@@ -31,7 +44,11 @@ for pos in [int(x) for x in ARGS.pos.split(",")]:
     for name in ARGS.impl.split(","):
         def call():
             h = h0.clone()
-            if name == "fused":
+            if name == "stream":
+                L.check(lib.mmvid_artv_decode_stream(layers16, NL, ops._ptr(h), ops._ptr(ws16), ops._ptr(lnw), ops._ptr(lnb),
+                                                     ops._ptr(head_w16), ops._ptr(head_b), ops._ptr(logits), 1024, B, D, H, S_max,
+                                                     pos, None, 1, st))
+            elif name == "fused":
                 L.check(lib.mmvid_artv_decode_fused(layers, NL, ops._ptr(h), ops._ptr(ws), ops._ptr(lnw), ops._ptr(lnb), ops._ptr(head_w),
                                                     ops._ptr(head_b), ops._ptr(logits), 1024, B, D, H, S_max, pos, st))
             elif name == "persistent":
