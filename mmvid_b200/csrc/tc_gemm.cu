@@ -762,9 +762,11 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
     // single-CTA tile; short-K GEMMs are bounded by their output stream and gain nothing).  MMVID_GEMM_2CTA=128|256
     // forces it everywhere, =1 disables it.
     const int bn2 = pick_pair_bn(M, N, K, tf32, c_dtype);
-    if (bn2 != 0 && g_qkv.q == nullptr)
-      return mmvid_linear_tc2(A, a_dtype, lda, W, w_dtype, ldw, bias, residual, ldr, C, c_dtype, ldc, M, N, K, act, precision,
-                              bn2, st);
+    if (bn2 != 0 && g_qkv.q == nullptr) {
+      const int rc = mmvid_linear_tc2(A, a_dtype, lda, W, w_dtype, ldw, bias, residual, ldr, C, c_dtype, ldc, M, N, K, act,
+                                      precision, bn2, st);
+      if (rc != 1) return rc;  // 1: not applicable (result cannot leave through TMA stores) -> single-CTA kernel below
+    }
   }
   const int BN = pick_bn(M, N, tf32);  // 256-wide tiles only pay in tf32 (r1s: bf16 c_fc 56 -> 68 us with them)
   CUtensorMap tmA, tmB;

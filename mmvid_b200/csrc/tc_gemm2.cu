@@ -21,8 +21,8 @@ namespace mmvid { extern unsigned long long* g_gemm_trace; }
 namespace {
 
 constexpr int BM = 128;  // rows per CTA (256 per pair)
-constexpr int G2_THREADS = 320;
-constexpr int EPI_WARPS = 8;
+constexpr int G2_THREADS = 576;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (four per TMEM lane quarter)
+constexpr int EPI_WARPS = 16;
 constexpr int EPI_LD = 32;
 
 struct Epi2Args {
@@ -101,13 +101,13 @@ __device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64
 }
 
 template <int BN>
-constexpr int g2_stages() { return BN == 256 ? 6 : (BN == 192 ? 6 : 8); }
+constexpr int g2_stages() { return BN == 256 ? 5 : (BN == 192 ? 5 : 6); }  // 64 KB of the 227 KB stage the results
 // TMEM columns to allocate for two BN-wide accumulators (the allocator wants a power of two)
 template <int BN>
 constexpr int g2_tmem_cols() { return 2 * BN <= 256 ? 256 : 512; }
 template <int BN>
 constexpr size_t g2_smem_bytes() {
-  return (size_t)g2_stages<BN>() * (BM * 128 + (BN / 2) * 128) + EPI_WARPS * 32 * EPI_LD * 4 + 1024 + 256;
+  return (size_t)g2_stages<BN>() * (BM * 128 + (BN / 2) * 128) + EPI_WARPS * 32 * EPI_LD * 4 + 1024 + 512;
 }
 
 // H16: the TMA-store epilogue writes 16-bit results (compile-time so that the fp32 epilogue keeps its register budget)
@@ -122,8 +122,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~(uintptr_t)1023);
+  uint64_t* res_bar = tmem_empty + 2;     // [EPI_WARPS] residual chunk landed in the warp's staging buffer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 512 + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = BM * 128, B_BYTES = (BN / 2) * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int BKE = TF32 ? 32 : 64;
   float* epi_stage = reinterpret_cast<float*>(tiles + (size_t)STAGES * STAGE_BYTES);
@@ -140,6 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EPI_WARPS); }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -203,157 +205,157 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       }
     }
   } else {
+    // ---------------- epilogue: warps 2..17.  TMEM lane quarter = warp % 4 (hardware rule), column part = (warp - 2) / 4:
+    // FOUR warps per SM sub-partition instead of two.  The r2f trace showed the 8-warp epilogue to need 13.4 k clk per
+    // 256 x 256 tile with QuickGELU (7.7 k without) against a 5.8 k clk fp16 main loop: two warps per sub-partition cannot
+    // hide the tcgen05.ld / MUFU / bulk-store latencies of a chunk behind each other.  Each warp now owns 1-2 32-column
+    // chunks of the tile (one 64-column group), a lane keeps its own output row: bias / QuickGELU / residual in registers,
+    // one write of the group into the warp's 4 KB staging buffer (SWIZZLE_128B layout), one bulk store; the TMA unit clips
+    // the M tail.  fp32 results leave per 32-column chunk, 16-bit results (H16) per group (tc_epilogue.cuh).
     const int q = warp & 3;
     const int ew = warp - 2;
-    const int chalf = ew >> 2;
-    if (e.tma_store) {
-      // ---- TMA-store epilogue (see tc_gemm.cu): a lane keeps its own output row, bias / activation / residual are applied
-      // in registers, each 32 x 32 chunk goes to shared memory once (SWIZZLE_128B layout) and leaves as one bulk store.
-      // The r1t trace showed the transposing epilogue below to take 17 k clk per 128 x 256 tile against a 10.7 k clk main
-      // loop: the 256-wide CTA-pair tile was epilogue bound by a wide margin.
-      const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 4096);
-      const uint32_t st_row = st_base + (uint32_t)(lane * 128);
-      constexpr int NCH = BN / 64;  // 32-column chunks per warp (half of the tile); 3 for the 192-wide tile
-      constexpr int GRP = NCH < 2 ? NCH : 2;
-      if (lane == 0) prefetch_tmap(&tmC);
-      uint32_t tile_iter = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
-        const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
-        const int m0 = mt * (2 * BM) + (int)rank * BM, n0 = nt * BN + chalf * (BN / 2);
-        const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
-        const long long m_row = (long long)m0 + q * 32 + lane;
-        const bool row_ok = m_row < e.M;
-        float4 res[GRP][8];
-        auto load_res = [&](int c0) {
+    const int cp = ew >> 2;
+    constexpr int TC = BN / 32;  // 32-column chunks per tile: 4 | 6 | 8
+    const int ch0 = cp * TC / 4, nch = (cp + 1) * TC / 4 - ch0;  // this warp's chunks [ch0, ch0 + nch), nch = 1 | 2
+    const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 4096);
+    const uint32_t st_row = st_base + (uint32_t)(lane * 128);
+    if (lane == 0) { prefetch_tmap(&tmC); prefetch_tmap(&tmQ); prefetch_tmap(&tmV); }
+    uint32_t tile_iter = 0, res_ph = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
+      const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
+      const int m0 = mt * (2 * BM) + (int)rank * BM;
+      const int n_grp0 = nt * BN + ch0 * 32;
+      const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+      const long long m_row = (long long)m0 + q * 32 + lane;
+      const bool row_ok = m_row < e.M;
+      int nvalid = 0;
+      for (int cc = 0; cc < nch; ++cc)
+        if (n_grp0 + cc * 32 < e.N) nvalid = cc + 1;
+      // fp32 results with a residual: the residual chunk is fetched by a TMA LOAD into the warp's staging buffer (coalesced,
+      // asynchronous, no registers) - for the first chunk before the accumulator is even complete -, the lanes add their
+      // own row in place and the buffer leaves again as the bulk store.  (Per-lane 16-byte loads of 32 different rows took
+      // ~8 k clk per chunk in the r2g trace: with ~1 KB of L1 left beside 227 KB of shared memory every load goes to L2.)
+      const bool res_tma = !H16 && e.residual != nullptr && e.qS == 0;
+      if (res_tma && nvalid > 0 && lane == 0) {
+        tma_store_wait_read();  // the buffer's previous bulk store has been read out
+        mbar_expect_tx(&res_bar[ew], 4096);
+        tma_load_2d(epi_stage + ew * 1024, &tmV, &res_bar[ew], n_grp0, m0 + q * 32);
+      }
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const bool etr = (warp == 2 && lane == 0);
+      if (etr) g2_stamp(e, tile_iter, 8);
+      const uint32_t t_src = tmem_base + acc * BN + ch0 * 32 + ((uint32_t)(q * 32) << 16);
+      // One chunk at a time (576 threads leave 96 registers per thread): the second chunk's tcgen05.ld is issued after the
+      // first has been processed, the accumulator is released as soon as this warp's last chunk is in registers.
+      // fused QKV scatter: groups start at multiples of 64 columns, so a group is the 64 head-dim values of ONE head of
+      // Q, K or V.  16-bit V^T groups are written straight from registers.
+      const bool vt_grp = H16 && e.qS > 0 && n_grp0 >= 2 * e.qH * 64;
+      if (H16 && !vt_grp && nvalid > 0) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll
-          for (int cc = 0; cc < GRP; ++cc) {
-            const int ncol = n0 + (c0 + cc) * 32;
+      for (int cc = 0; cc < 2; ++cc) {
+        if (cc >= nch) continue;  // warp-uniform
+        uint32_t racc[32];
+        tmem_ld32(t_src + cc * 32, racc);
+        tmem_ld_wait();
+        if (cc == nch - 1) {
+          // this warp's share of the accumulator is in registers: release it (leader's barrier, 2 x 16 arrivals)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+          if (etr) g2_stamp(e, tile_iter, 9);
+        }
+        if (cc >= nvalid) continue;  // columns beyond N (warp-uniform)
+        const int ncol = n_grp0 + cc * 32;
+        float o[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              res[cc][i] = (row_ok && c0 + cc < NCH && ncol < e.N) ? *reinterpret_cast<const float4*>(e.residual + m_row * e.ldr + ncol + 4 * i)
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + 4 * i));
+          o[4 * i + 0] = __uint_as_float(racc[4 * i + 0]) + b.x;
+          o[4 * i + 1] = __uint_as_float(racc[4 * i + 1]) + b.y;
+          o[4 * i + 2] = __uint_as_float(racc[4 * i + 2]) + b.z;
+          o[4 * i + 3] = __uint_as_float(racc[4 * i + 3]) + b.w;
+        }
+        if (e.act != MMVID_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = apply_act_fast(o[i], e.act);
+        }
+        if (res_tma) {
+          if (cc == 1 && lane == 0) {  // second chunk: its residual can only land once the first chunk's store has been read out
+            tma_store_wait_read();
+            mbar_expect_tx(&res_bar[ew], 4096);
+            tma_load_2d(epi_stage + ew * 1024, &tmV, &res_bar[ew], ncol, m0 + q * 32);
           }
-        };
-        if (e.residual) load_res(0);
-        mbar_wait(&tmem_full[acc], acc_ph);
-        tc_fence_after();
-        const bool etr = (warp == 2 && lane == 0);
-        if (etr) g2_stamp(e, tile_iter, 8);
-        const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
+          mbar_wait(&res_bar[ew], res_ph);
+          res_ph ^= 1u;
 #pragma unroll
-        for (int c0 = 0; c0 < NCH; c0 += GRP) {
-          uint32_t racc[GRP][32];
+          for (int j = 0; j < 8; ++j) {
+            const float4 r4 = lds128(st_row + (uint32_t)((j ^ (lane & 7)) * 16));
+            o[4 * j + 0] += r4.x; o[4 * j + 1] += r4.y; o[4 * j + 2] += r4.z; o[4 * j + 3] += r4.w;
+          }
+        } else if (e.residual && row_ok) {
 #pragma unroll
-          for (int cc = 0; cc < GRP; ++cc)
-            if (c0 + cc < NCH) tmem_ld32(t_src + (c0 + cc) * 32, racc[cc]);
-          tmem_ld_wait();
-          if (c0 + GRP >= NCH) {  // the whole accumulator is in registers: release it (leader's barrier, 16 arrivals)
-            tc_fence_before();
+          for (int i = 0; i < 8; ++i) {
+            const float4 r4 = *reinterpret_cast<const float4*>(e.residual + m_row * e.ldr + ncol + 4 * i);
+            o[4 * i + 0] += r4.x; o[4 * i + 1] += r4.y; o[4 * i + 2] += r4.z; o[4 * i + 3] += r4.w;
+          }
+        }
+        if constexpr (H16) {
+          const bool f16 = e.c_h16 == 2;
+          if (vt_grp) {
+            // for a fixed head-dim index the 32 lanes write 32 consecutive tokens: one coalesced 64-byte store
+            const int hh = (ncol - 2 * e.qH * 64) >> 6, d0 = ncol & 63;
+            if (row_ok) {
+              const int b2 = (int)(m_row / e.qS), s2 = (int)(m_row - (long long)b2 * e.qS);
+              uint16_t* dst = reinterpret_cast<uint16_t*>(e.qkv_vt) + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
+#pragma unroll
+              for (int d = 0; d < 32; ++d) dst[(long long)d * e.qSpad] = cvt_h16_rt(o[d], f16);
+            }
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t u0 = pack_h16_rt(o[8 * j + 0], o[8 * j + 1], f16), u1 = pack_h16_rt(o[8 * j + 2], o[8 * j + 3], f16);
+            const uint32_t u2 = pack_h16_rt(o[8 * j + 4], o[8 * j + 5], f16), u3 = pack_h16_rt(o[8 * j + 6], o[8 * j + 7], f16);
+            uint32_t addr;
+            if (nvalid == 2) addr = st_row + (uint32_t)(((cc * 4 + j) ^ (lane & 7)) * 16);
+            else addr = st_base + (uint32_t)(lane * 64 + j * 16);  // lone chunk: dense 64-byte rows (SWIZZLE_NONE map)
+            sts128_u32(addr, u0, u1, u2, u3);
+          }
+        } else {
+          if (!res_tma) {
+            if (lane == 0) tma_store_wait_read();  // the previous chunk's bulk store has finished READING the staging buffer
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
-            if (etr) g2_stamp(e, tile_iter, 9);
           }
-          // 16-bit results (H16): the group's chunks are packed and staged one after the other and leave together as one
-          // {64 x 32} box (128-byte rows); a lone chunk leaves as a {32 x 32} box (tc_epilogue.cuh)
-          const int n_grp0 = n0 + c0 * 32;
-          int nvalid = 0;
+          if (e.qS > 0) {
+            // ---- fused QKV scatter (fp32).  A chunk is 32 tokens x 32 columns of one head: Q / K chunks are stored as they
+            // are into [B*H, S_pad, 64] by one 3-D TMA store.  Chunks whose 32 tokens straddle a batch boundary (or the end
+            // of the last batch) are written row by row from registers: a TMA box cannot be clipped at S < S_pad, and the
+            // padding rows must stay zero.  V^T chunks always go out from registers: for a fixed head-dim index the 32 lanes
+            // write 32 consecutive tokens (one coalesced 128-byte store), and a TMA box into V^T would need its first token
+            // 16-byte aligned, which an odd S rules out for every batch but the first.
+            const int D = e.qH * 64;
+            const int which = ncol / D, hh = (ncol - which * D) >> 6, d0 = ncol & 63;
+            const int mb = m0 + q * 32;
+            const int bb = mb / e.qS, ss0 = mb - bb * e.qS;
+            if (which == 2 || ss0 + 32 > e.qS || bb >= e.qB) {  // warp-uniform
+              if (row_ok) {
+                const int b2 = (int)(m_row / e.qS), s2 = (int)(m_row - (long long)b2 * e.qS);
+                if (which < 2) {
+                  float* dst = reinterpret_cast<float*>(which == 0 ? e.qkv_q : e.qkv_k) + (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64 + d0;
 #pragma unroll
-          for (int cc = 0; cc < GRP; ++cc)
-            if (c0 + cc < NCH && n_grp0 + cc * 32 < e.N) nvalid = cc + 1;
-          // fused QKV scatter: groups start at multiples of 64 columns, so a group is the 64 head-dim values of ONE head of
-          // Q, K or V.  V^T groups are written straight from registers.
-          const bool vt_grp = H16 && e.qS > 0 && n_grp0 >= 2 * e.qH * 64;
-          if (H16 && !vt_grp && nvalid > 0) {
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-          }
+                  for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                } else {
+                  float* dst = reinterpret_cast<float*>(e.qkv_vt) + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
 #pragma unroll
-          for (int cc = 0; cc < GRP; ++cc) {
-            const int ncol = n0 + (c0 + cc) * 32;
-            if (c0 + cc >= NCH || ncol >= e.N) continue;  // warp-uniform
-            float o[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + 4 * i));
-              o[4 * i + 0] = __uint_as_float(racc[cc][4 * i + 0]) + b.x;
-              o[4 * i + 1] = __uint_as_float(racc[cc][4 * i + 1]) + b.y;
-              o[4 * i + 2] = __uint_as_float(racc[cc][4 * i + 2]) + b.z;
-              o[4 * i + 3] = __uint_as_float(racc[cc][4 * i + 3]) + b.w;
-            }
-            if (e.act != MMVID_ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = apply_act_fast(o[i], e.act);
-            }
-            if (e.residual) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                o[4 * i + 0] += res[cc][i].x; o[4 * i + 1] += res[cc][i].y;
-                o[4 * i + 2] += res[cc][i].z; o[4 * i + 3] += res[cc][i].w;
-              }
-            }
-            if constexpr (H16) {
-              const bool f16 = e.c_h16 == 2;
-              if (vt_grp) {
-                // for a fixed head-dim index the 32 lanes write 32 consecutive tokens: one coalesced 64-byte store
-                const int hh = (ncol - 2 * e.qH * 64) >> 6, d0 = ncol & 63;
-                const long long m = (long long)m0 + q * 32 + lane;
-                if (m < e.M) {
-                  const int b2 = (int)(m / e.qS), s2 = (int)(m - (long long)b2 * e.qS);
-                  uint16_t* dst = reinterpret_cast<uint16_t*>(e.qkv_vt) + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
-#pragma unroll
-                  for (int d = 0; d < 32; ++d) dst[(long long)d * e.qSpad] = cvt_h16_rt(o[d], f16);
+                  for (int d = 0; d < 32; ++d) dst[(long long)d * e.qSpad] = o[d];
                 }
-                continue;
               }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t u0 = pack_h16_rt(o[8 * j + 0], o[8 * j + 1], f16), u1 = pack_h16_rt(o[8 * j + 2], o[8 * j + 3], f16);
-                const uint32_t u2 = pack_h16_rt(o[8 * j + 4], o[8 * j + 5], f16), u3 = pack_h16_rt(o[8 * j + 6], o[8 * j + 7], f16);
-                uint32_t addr;
-                if (nvalid == 2) addr = st_row + (uint32_t)(((cc * 4 + j) ^ (lane & 7)) * 16);
-                else addr = st_base + (uint32_t)(lane * 64 + j * 16);  // lone chunk: dense 64-byte rows (SWIZZLE_NONE map)
-                sts128_u32(addr, u0, u1, u2, u3);
-              }
-              continue;
-            } else {
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-            if (e.qS > 0) {
-              // ---- fused QKV scatter.  A chunk is 32 tokens x 32 columns of one head (32 | 64): Q / K chunks are stored as
-              // they are into [B*H, S_pad, 64] by one 3-D TMA store.  The few chunks whose 32 tokens straddle a batch
-              // boundary (or the end of the last batch) are written row by row from registers instead: a TMA box cannot
-              // be clipped at S < S_pad, and the padding rows / columns must stay zero.
-              const int D = e.qH * 64;
-              const int which = ncol / D, hh = (ncol - which * D) >> 6, d0 = ncol & 63;
-              const int mb = m0 + q * 32;
-              const int bb = mb / e.qS, ss0 = mb - bb * e.qS;
-              // V^T chunks always go out from registers: for a fixed head-dim index the 32 lanes write 32 consecutive
-              // tokens (one coalesced 128-byte store), and a TMA box into V^T would need its first token 16-byte aligned,
-              // which an odd S rules out for every batch but the first (found the hard way: 'illegal instruction').
-              if (which == 2 || ss0 + 32 > e.qS || bb >= e.qB) {  // warp-uniform
-                const long long m = (long long)mb + lane;
-                if (m < e.M) {
-                  const int b2 = (int)(m / e.qS), s2 = (int)(m - (long long)b2 * e.qS);
-                  if (which < 2) {
-                    float* dst = reinterpret_cast<float*>(which == 0 ? e.qkv_q : e.qkv_k) + (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64 + d0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                      *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                  } else {
-                    float* dst = reinterpret_cast<float*>(e.qkv_vt) + (((long long)b2 * e.qH + hh) * 64 + d0) * e.qSpad + s2;
-#pragma unroll
-                    for (int d = 0; d < 32; ++d) dst[(long long)d * e.qSpad] = o[d];
-                  }
-                }
-                continue;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) tma_store_3d(which == 0 ? &tmQ : &tmK, st_base, d0, ss0, bb * e.qH + hh);
               continue;
             }
 #pragma unroll
@@ -361,144 +363,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
               sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) tma_store_2d(&tmC, st_base, ncol, m0 + q * 32);
-            }  // !H16
+            if (lane == 0) tma_store_3d(which == 0 ? &tmQ : &tmK, st_base, d0, ss0, bb * e.qH + hh);
+            continue;
           }
-          if (H16 && !vt_grp && nvalid > 0) {
-            if (e.qS > 0) {
-              // Q / K group: one {64, 32, 1} box, or row by row where the 32 tokens straddle a batch boundary (a TMA box
-              // cannot be clipped at S < S_pad, and the padding rows must stay zero)
-              const int D = e.qH * 64;
-              const int which = n_grp0 / D, hh = (n_grp0 - which * D) >> 6;
-              const int mb = m0 + q * 32;
-              const int bb = mb / e.qS, ss0 = mb - bb * e.qS;
-              if (ss0 + 32 > e.qS || bb >= e.qB) {  // warp-uniform
-                __syncwarp();
-                const long long m = (long long)mb + lane;
-                if (m < e.M) {
-                  const int b2 = (int)(m / e.qS), s2 = (int)(m - (long long)b2 * e.qS);
-                  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(which == 0 ? e.qkv_q : e.qkv_k) +
-                                                        (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64);
 #pragma unroll
-                  for (int u = 0; u < 8; ++u) {  // this lane's own staged row
-                    const float4 v = lds128(st_row + (uint32_t)((u ^ (lane & 7)) * 16));
-                    dst[u] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-                  }
-                }
-                __syncwarp();
-              } else {
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tma_store_3d(which == 0 ? &tmQ : &tmK, st_base, 0, ss0, bb * e.qH + hh);
-              }
-            } else {
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) tma_store_2d(nvalid == 2 ? &tmC : &tmQ /* {32 x 32} box */, st_base, n_grp0, m0 + q * 32);
-            }
-          }
-          if (e.residual && c0 + GRP < NCH) load_res(c0 + GRP);
-        }
-        if (etr) g2_stamp(e, tile_iter, 10);
-      }
-      if (lane == 0) tma_store_wait_all();
-      __syncwarp();
-    } else {
-    const uint32_t st_base = smem_u32(epi_stage) + (uint32_t)(ew * 32 * EPI_LD * 4);
-    const uint32_t st_wr = st_base + (uint32_t)(lane * EPI_LD * 4);
-    const int col = (lane & 7) * 4, rsub = lane >> 3;
-    const uint32_t st_rd_row = st_base + (uint32_t)(rsub * EPI_LD * 4);
-    const bool vec_ok = (e.N % 4 == 0) && (e.ldc % 4 == 0) && (!e.residual || e.ldr % 4 == 0);
-    constexpr int NCH = BN / 64;  // 32-column chunks per warp (half of the tile); 3 for the 192-wide tile
-    uint32_t tile_iter = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
-      const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
-      const int m0 = mt * (2 * BM) + (int)rank * BM, n0 = nt * BN + chalf * (BN / 2);
-      const uint32_t acc = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
-      float4 bias_r[NCH];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int n = n0 + c * 32 + col;
-        bias_r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias && n < e.N) {
-          if (vec_ok) bias_r[c] = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-          else {
-            bias_r[c].x = e.bias[n];
-            if (n + 1 < e.N) bias_r[c].y = e.bias[n + 1];
-            if (n + 2 < e.N) bias_r[c].z = e.bias[n + 2];
-            if (n + 3 < e.N) bias_r[c].w = e.bias[n + 3];
-          }
-        }
-      }
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
-      const bool etr = (warp == 2 && lane == 0);
-      if (etr) g2_stamp(e, tile_iter, 8);
-      const uint32_t t_src = tmem_base + acc * BN + chalf * (BN / 2) + ((uint32_t)(q * 32) << 16);
-      const long long m_first = (long long)m0 + q * 32 + rsub;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_src + c * 32, r);
-        tmem_ld_wait();
-        if (c == NCH - 1) {  // everything this warp needs is out of TMEM: release the accumulator (leader's barrier)
-          tc_fence_before();
+          for (int j = 0; j < 8; ++j)  // 16-byte unit j of row r lives at unit j ^ (r & 7): the TMA 128-byte swizzle
+            sts128(st_row + (uint32_t)((j ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+          if (lane == 0) tma_store_2d(&tmC, st_base, ncol, m0 + q * 32);
         }
-        if (n0 + c * 32 >= e.N) continue;
+      }
+      if (H16 && !vt_grp && nvalid > 0) {
+        if (e.qS > 0) {
+          // Q / K group: one {64, 32, 1} box, or row by row where the 32 tokens straddle a batch boundary
+          const int D = e.qH * 64;
+          const int which = n_grp0 / D, hh = (n_grp0 - which * D) >> 6;
+          const int mb = m0 + q * 32;
+          const int bb = mb / e.qS, ss0 = mb - bb * e.qS;
+          if (ss0 + 32 > e.qS || bb >= e.qB) {  // warp-uniform
+            __syncwarp();
+            if (row_ok) {
+              const int b2 = (int)(m_row / e.qS), s2 = (int)(m_row - (long long)b2 * e.qS);
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(which == 0 ? e.qkv_q : e.qkv_k) +
+                                                    (((long long)b2 * e.qH + hh) * e.qSpad + s2) * 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(st_wr + (uint32_t)(((j ^ (lane & 7)) * 16)), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        __syncwarp();
-        const int n = n0 + c * 32 + col;
-        const bool n_ok = n < e.N;
-        float4 res[8], v[8];
-        if (vec_ok && e.residual) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const long long m = m_first + i * 4;
-            res[i] = (m < e.M && n_ok) ? *reinterpret_cast<const float4*>(e.residual + m * e.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          v[i] = lds128(st_rd_row + (uint32_t)(i * 4 * EPI_LD * 4) + (uint32_t)((((lane & 7) ^ ((rsub + 4 * i) & 7)) * 16)));
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long m = m_first + i * 4;
-          if (m >= e.M || !n_ok) continue;
-          float o[4] = {v[i].x + bias_r[c].x, v[i].y + bias_r[c].y, v[i].z + bias_r[c].z, v[i].w + bias_r[c].w};
-          if (e.act != MMVID_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = apply_act_fast(o[j], e.act);
-          }
-          if (vec_ok) {
-            if (e.residual) { o[0] += res[i].x; o[1] += res[i].y; o[2] += res[i].z; o[3] += res[i].w; }
-            if (e.c_h16) {
-              uint2 pk;
-              pk.x = pack_h16_rt(o[0], o[1], e.c_h16 == 2);
-              pk.y = pack_h16_rt(o[2], o[3], e.c_h16 == 2);
-              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.C) + m * e.ldc + n) = pk;
-            } else {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + m * e.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+              for (int u = 0; u < 8; ++u) {  // this lane's own staged row
+                const float4 v = lds128(st_row + (uint32_t)((u ^ (lane & 7)) * 16));
+                dst[u] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+              }
             }
+            __syncwarp();
           } else {
-            for (int j = 0; j < 4; ++j) {
-              if (n + j >= e.N) break;
-              float x = o[j];
-              if (e.residual) x += e.residual[m * e.ldr + n + j];
-              if (e.c_h16) reinterpret_cast<uint16_t*>(e.C)[m * e.ldc + n + j] = cvt_h16_rt(x, e.c_h16 == 2);
-              else reinterpret_cast<float*>(e.C)[m * e.ldc + n + j] = x;
-            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tma_store_3d(which == 0 ? &tmQ : &tmK, st_base, 0, ss0, bb * e.qH + hh);
           }
+        } else {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(nvalid == 2 ? &tmC : &tmQ /* {32 x 32} box */, st_base, n_grp0, m0 + q * 32);
         }
-        __syncwarp();
       }
       if (etr) g2_stamp(e, tile_iter, 10);
     }
-    }  // !tma_store
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   }
   tc_fence_before();
   cluster_sync_all();
@@ -512,7 +422,8 @@ struct QkvMaps { CUtensorMap q, k, v; };
 
 template <bool TF32, int BN, bool H16>
 int launch2k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmQ,
-             const CUtensorMap& tmK, const Epi2Args& e, int clusters, const char* what, cudaStream_t st) {
+             const CUtensorMap& tmK, const CUtensorMap& tmR, const Epi2Args& e, int clusters, const char* what,
+             cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = g2_smem_bytes<BN>();
   if (!attr_set) {
@@ -520,7 +431,7 @@ int launch2k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(err));
     attr_set = true;
   }
-  gemm_tc2_kernel<TF32, BN, H16><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, tmQ, tmK, tmA, e);
+  gemm_tc2_kernel<TF32, BN, H16><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, tmQ, tmK, tmR, e);
   return check_launch(what);
 }
 
@@ -533,12 +444,11 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStre
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = (long long)e.num_m_tiles * e.num_n_tiles;
   const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
-  CUtensorMap tmC = tmA, tmC1 = tmA;  // placeholders when unused
+  CUtensorMap tmC = tmA, tmC1 = tmA, tmR = tmA;  // placeholders when unused
   e.tma_store = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const char* ts = getenv("MMVID_GEMM_TMA_STORE");
   const int csz = e.c_h16 ? 2 : 4;
-  if (qm == nullptr && !(ts && ts[0] == '0') && !(TF32 && e.c_h16) && e.N % 32 == 0 && (e.ldc * csz) % 16 == 0 && al16(e.C) &&
+  if (qm == nullptr && !(TF32 && e.c_h16) && e.N % 32 == 0 && (e.ldc * csz) % 16 == 0 && al16(e.C) &&
       (!e.residual || (e.ldr % 4 == 0 && al16(e.residual))) && (!e.bias || al16(e.bias))) {
     uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
     uint64_t str[1] = {(uint64_t)e.ldc * csz};
@@ -554,25 +464,32 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, Epi2Args e, cudaStre
       uint32_t box[2] = {32, 32};
       int rc = make_tensor_map(&tmC, e.C, DT_F32_EXACT, 2, dims, str, box);
       if (rc) return rc;
+      if (e.residual) {  // fetched chunk by chunk through the same kind of box (may be C itself: in-place residual add)
+        uint64_t rstr[1] = {(uint64_t)e.ldr * 4};
+        rc = make_tensor_map(&tmR, e.residual, DT_F32_EXACT, 2, dims, rstr, box);
+        if (rc) return rc;
+      }
     }
     e.tma_store = 1;
   }
   if (qm != nullptr) {
     e.tma_store = 1;  // the QKV scatter only exists in the TMA-store epilogue (the caller checked its preconditions)
     if constexpr (!TF32) {
-      if (e.c_h16) return launch2k<TF32, BN, true>(tmA, tmB, tmA, qm->q, qm->k, e, clusters, "gemm_tc2_qkv", st);
+      if (e.c_h16) return launch2k<TF32, BN, true>(tmA, tmB, tmA, qm->q, qm->k, tmA, e, clusters, "gemm_tc2_qkv", st);
     }
-    return launch2k<TF32, BN, false>(tmA, tmB, tmA, qm->q, qm->k, e, clusters, "gemm_tc2_qkv", st);
+    return launch2k<TF32, BN, false>(tmA, tmB, tmA, qm->q, qm->k, tmA, e, clusters, "gemm_tc2_qkv", st);
   }
+  if (!e.tma_store) return 1;  // results leave through TMA bulk stores only: the caller uses the single-CTA kernel instead
   if constexpr (!TF32) {
-    if (e.c_h16 && e.tma_store) return launch2k<TF32, BN, true>(tmA, tmB, tmC, tmC1, tmA, e, clusters, "gemm_tc2", st);
+    if (e.c_h16) return launch2k<TF32, BN, true>(tmA, tmB, tmC, tmC1, tmA, tmR, e, clusters, "gemm_tc2", st);
   }
-  return launch2k<TF32, BN, false>(tmA, tmB, tmC, tmC1, tmA, e, clusters, "gemm_tc2", st);
+  return launch2k<TF32, BN, false>(tmA, tmB, tmC, tmC1, tmA, tmR, e, clusters, "gemm_tc2", st);
 }
 
 }  // namespace
 
-// 2-CTA path of mmvid_linear (selected by mmvid_linear_tc: MMVID_GEMM_2CTA=BN in the environment, 128 or 256)
+// 2-CTA path of mmvid_linear (selected by mmvid_linear_tc).  Returns 1 ("not applicable") when the result cannot leave
+// through TMA bulk stores (N % 32, alignment, fp32 operands with a 16-bit result): the caller then runs the single-CTA kernel.
 extern "C" int mmvid_linear_tc2(const void* A, int a_dtype, long long lda, const void* W, int w_dtype, long long ldw,
                                 const float* bias, const float* residual, long long ldr, void* C, int c_dtype,
                                 long long ldc, long long M, int N, int K, int act, int precision, int BN, cudaStream_t st) {
