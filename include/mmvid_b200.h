@@ -268,6 +268,22 @@ int mmvid_transpose2d(const float* in, float* out, int R, int C, mmvid_stream_t 
  * stamps of its pipeline events into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/att_trace.py. */
 int mmvid_debug_attention_trace(unsigned long long* dev_buf);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident mask-predict sampling (BERT.mask_predict, dalle_bert.py:527-538, 646-691; sampling_mode 'batched').
+ * Philox4x32-10 keyed by (seed, row | item, offset): same seed / offset => same draw.
+ *   mmvid_mp_sample: per row of n logits (n % 128 == 0, <= 1024):  probs = softmax(logits + noise_scale * gumbel);
+ *     tok ~ Categorical(probs);  Y = probs[tok].  Rows with skip[row] != 0 keep their Y / tok (tokens kept from the
+ *     previous iteration).  skip may be NULL.
+ *   mmvid_mp_keep: per (sample, beam): keep k of the tokens with pmask == 0 WITHOUT replacement, probability proportional
+ *     to Y (Gumbel-top-k == torch.multinomial(Y, k, replacement=False) in distribution); tokens with pmask != 0 are always
+ *     kept.  keep [samples*beams, Ttot] (uint8), ids_in = keep ? I_tok : mask_id.  Y, I_tok: [samples, Ttot].
+ * ---------------------------------------------------------------------------------------------- */
+int mmvid_mp_sample(const float* logits, long long rows, int n, float noise_scale, const uint8_t* skip, float* Y,
+                    int64_t* tok, unsigned long long seed, unsigned long long offset, mmvid_stream_t stream);
+int mmvid_mp_keep(const float* Y, const uint8_t* pmask, const int64_t* I_tok, int samples, int beams, int Ttot, int k,
+                  long long mask_id, uint8_t* keep, int64_t* ids_in, unsigned long long seed, unsigned long long offset,
+                  mmvid_stream_t stream);
+
 /* Profiling hook: CTA 0 of every following mmvid_artv_decode_stream launch writes %globaltimer (ns) stamps of its phase
  * events into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/decode_trace.py. */
 int mmvid_debug_decode_trace(unsigned long long* dev_buf);

@@ -533,8 +533,11 @@ class BERT(nn.Module):
                      mp_config=None, long_mode="long", **kwargs):
         """dalle_bert.py:514-714 -> (long [B, target_seq_len], image_samples)."""
         mp_config = dict(DEFAULT_MP_CONFIG) if mp_config is None else mp_config
-        if self.sampling_mode == "batched" and mp_config["B"] == 1 and not dynamic and not debug:
-            return self._mask_predict_batched(control_emb, steps, preserve, t_overlap, mp_config, long_mode), []
+        if self.sampling_mode == "batched" and not debug:
+            import os
+            if os.environ.get("MMVID_SAMPLER", "device") == "torch" and mp_config["B"] == 1 and not dynamic:
+                return self._mask_predict_batched(control_emb, steps, preserve, t_overlap, mp_config, long_mode), []
+            return self._mask_predict_device(control_emb, steps, preserve, t_overlap, mp_config, long_mode, dynamic), []
         dev = control_emb.device
         nb, csl, D = control_emb.shape
         Ttot = self.target_seq_len
@@ -625,17 +628,26 @@ class BERT(nn.Module):
         logits head captured in one CUDA graph.  Static buffers: the caller fills x[:, :control] and ids, replays,
         and reads logits before the next replay (same stream)."""
         key = (nb, str(dev), str(self.precision), str(self.transformer.precision), self._weights_version())
-        ent = getattr(self, "_graph_cache", None)
-        if ent is not None and ent["key"] == key:
+        cache = getattr(self, "_graph_cache", None)
+        if cache is None or not isinstance(cache, dict) or cache.get("_sig") != key[1:]:
+            cache = self._graph_cache = {"_sig": key[1:]}  # new weights / precision / device: drop every captured graph
+        ent = cache.get(nb)
+        if ent is not None:
             return ent
+        while len(cache) > 4:  # "_sig" + at most 3 batch sizes (first step, beams, a second caller)
+            cache.pop(next(k for k in cache if k != "_sig"))
         D, Ttot, csl = self.dim, self.target_seq_len, self.control_seq_len
         x = torch.zeros(nb, self.total_seq_len, D, device=dev, dtype=torch.float32)
         ids = torch.full((nb, Ttot), self.image_token_lut["[MASK]"], dtype=torch.long, device=dev)
 
+        score_idx = torch.tensor([self.rel_tok_index, self.vid_tok_index], device=dev)
+
         def fwd():
             ops.embed_gather(x, [self._target_segment(ids)])
             out = self.transformer(x)
-            return self._head(out[:, csl:].reshape(nb * Ttot, D), self.to_logits).view(nb, Ttot, -1)
+            # [REL] / [VID] rows for the beam / dynamic-stop scores (dalle_bert.py:685-689)
+            return (self._head(out[:, csl:].reshape(nb * Ttot, D), self.to_logits).view(nb, Ttot, -1),
+                    out.index_select(1, score_idx).contiguous())
 
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
@@ -648,14 +660,115 @@ class BERT(nn.Module):
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
-            logits = fwd()
+            logits, score_rows = fwd()
         # The graph holds raw pointers: keep every tensor it reads or writes alive for as long as the graph lives, even if
         # a later forward of another shape makes the transformer replace its cached Q / K / V^T buffers or bf16 copies.
         keep = [getattr(self.transformer, "_qkv_bufs", None), self.target_pos_emb.table(),
-                list(self.transformer._bf16._d.values())]
-        ent = dict(key=key, graph=graph, x=x, ids=ids, logits=logits, launches=_lib.launch_count() - n0, keep=keep)
-        self._graph_cache = ent
+                list(self.transformer._bf16._d.values()), score_idx]
+        ent = dict(key=key, graph=graph, x=x, ids=ids, logits=logits, score_rows=score_rows,
+                   launches=_lib.launch_count() - n0, keep=keep)
+        cache[nb] = ent
         return ent
+
+    def _mask_predict_device(self, control_emb, steps, preserve, t_overlap, mp_config, long_mode, dynamic):
+        """Device-resident mask-predict (the 'batched' sampling mode): every sample and every beam advances in the same
+        forward, both random draws of an iteration are one kernel each (csrc/sampling.cu), beam scoring, beam choice and the
+        dynamic-stop bookkeeping stay on the device - no host synchronisation anywhere in the loop.  Same algorithm and
+        distributions as the reference loop (dalle_bert.py:618-711); its own Philox streams, seeded from torch's CPU
+        generator (so torch.manual_seed makes it reproducible), instead of torch's call order.  A sample whose dynamic stop
+        has fired (t - tmax >= 5) is frozen rather than left out: the loop always runs Tmax iterations."""
+        dev = control_emb.device
+        nb, csl, D = control_emb.shape
+        Ttot = self.target_seq_len
+        MASK = self.image_token_lut["[MASK]"]
+        N, pmask, ptok = self._preserve_setup(nb, preserve, t_overlap, long_mode, dev)
+        Tmax = mp_config["T"] if steps <= 0 else steps
+        Bm = int(mp_config["B"])
+        n, temp = mask_predict_schedules(N, mp_config)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator: no device sync
+        scoring = dynamic or Bm > 1
+        use_graph = self._use_cuda_graph(dev)
+        from . import _lib as _lib_mod
+
+        def make_runner(batch, control):
+            if use_graph:
+                fg = self._forward_graph(batch, dev)
+                fg["x"][:, :csl].copy_(control)
+
+                def run(ids_in):
+                    fg["ids"].copy_(ids_in)
+                    fg["graph"].replay()
+                    _lib_mod.add_launch_count(fg["launches"])
+                    return fg["logits"], fg["score_rows"]
+                return run
+            xb = torch.empty(batch, self.total_seq_len, D, device=dev, dtype=torch.float32)
+            xb[:, :csl].copy_(control)
+            sidx = torch.tensor([self.rel_tok_index, self.vid_tok_index], device=dev)
+
+            def run(ids_in):
+                ops.embed_gather(xb, [self._target_segment(ids_in)])
+                out = self.transformer(xb)
+                return (self._head(out[:, csl:].reshape(batch * Ttot, D), self.to_logits).view(batch, Ttot, -1),
+                        out.index_select(1, sidx).contiguous())
+            return run
+
+        run1 = make_runner(nb, control_emb)
+        tok_in = torch.where(pmask, ptok, torch.full_like(ptok, MASK))
+        logits, _ = run1(tok_in)
+        Y = torch.empty(nb, Ttot, device=dev, dtype=torch.float32)
+        I_tok = torch.empty(nb, Ttot, device=dev, dtype=torch.long)
+        ops.mp_sample(logits, Y, I_tok, seed, 0, noise_scale=temp[0])
+        I_tok = torch.where(pmask, ptok, I_tok)
+        if Tmax <= 1:
+            if dynamic:
+                raise RuntimeError("mask_predict: dynamic=True needs at least 2 steps (the reference returns None here)")
+            return I_tok
+        runB = run1 if Bm == 1 else make_runner(nb * Bm, control_emb.repeat_interleave(Bm, 0))
+        pm_row = pmask[0].contiguous()
+        Imax = I_tok
+        if dynamic:
+            Smax = torch.zeros(nb, device=dev)
+            tmax = torch.zeros(nb, device=dev, dtype=torch.long)
+            active = torch.ones(nb, device=dev, dtype=torch.bool)
+            ar = torch.arange(nb, device=dev)
+        elif Bm > 1:
+            ar = torch.arange(nb, device=dev)
+        for t in range(1, Tmax):
+            k = max(N - n[t - 1], 1)
+            keep, ids_in = ops.mp_keep(Y, pm_row, I_tok, k, MASK, seed, 2 * t - 1, beams=Bm)
+            logits, score_rows = runB(ids_in)
+            if not scoring:
+                # tokens that were not kept get a new draw; kept ones stay (dalle_bert.py:682-684)
+                ops.mp_sample(logits, Y, I_tok, seed, 2 * t, noise_scale=temp[t], skip=keep)
+                Imax = I_tok
+                continue
+            Ynew = torch.empty(nb * Bm, Ttot, device=dev, dtype=torch.float32)
+            Inew = torch.empty(nb * Bm, Ttot, device=dev, dtype=torch.long)
+            ops.mp_sample(logits, Ynew, Inew, seed, 2 * t, noise_scale=temp[t], skip=keep)
+            keepv, Ynew, Inew = keep.view(nb, Bm, Ttot), Ynew.view(nb, Bm, Ttot), Inew.view(nb, Bm, Ttot)
+            YB, IB = [], []
+            for j in range(Bm):  # beam j starts from beam j-1's state (the reference's cumulative update, :676-684)
+                Y = torch.where(keepv[:, j], Y, Ynew[:, j])
+                I_tok = torch.where(keepv[:, j], I_tok, Inew[:, j])
+                YB.append(Y)
+                IB.append(I_tok)
+            s_rel = torch.sigmoid(self._head_scalar(score_rows[:, 0].contiguous(), self.to_logits_rel))
+            s_vid = torch.sigmoid(self._head_scalar(score_rows[:, 1].contiguous(), self.to_logits_vid))
+            S = (0.5 * s_rel + 0.5 * s_vid).view(nb, Bm)
+            jmax = S.argmax(dim=1)
+            if Bm > 1:
+                Y = torch.stack(YB, 1)[ar, jmax]
+                I_tok = torch.stack(IB, 1)[ar, jmax]
+            if dynamic:
+                Sbest = S.gather(1, jmax.view(nb, 1)).view(nb)
+                better = (Sbest > Smax) & active
+                Smax = torch.where(better, Sbest, Smax)
+                tmax = torch.where(better, torch.full_like(tmax, t), tmax)
+                Imax = torch.where(better.view(nb, 1), I_tok, Imax)
+                active = active & ((t - tmax) < 5)
+            else:
+                Imax = I_tok
+        return Imax
 
     def _mask_predict_batched(self, control_emb, steps, preserve, t_overlap, mp_config, long_mode):
         """Throughput variant of mask_predict: every sample advances in the same [B,S,D] forward.  Same algorithm

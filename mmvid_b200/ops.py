@@ -195,6 +195,41 @@ def softmax_logits(logits, noise=None, noise_scale=0.0):
     return probs.view_as(logits)
 
 
+def mp_sample(logits, Y, tok, seed, offset, noise_scale=0.0, skip=None):
+    """Fused softmax + categorical draw + gather per row of `logits` [..., n] (dalle_bert.py:527-534); updates Y (float32)
+    and tok (int64) of the rows whose `skip` flag (uint8 / bool) is not set."""
+    lib = L.load()
+    _req(logits, torch.float32)
+    n = logits.shape[-1]
+    l2 = logits.reshape(-1, n)
+    assert l2.is_contiguous() and Y.is_contiguous() and tok.is_contiguous() and Y.numel() == l2.shape[0] == tok.numel()
+    assert Y.dtype == torch.float32 and tok.dtype == torch.int64
+    if skip is not None:
+        skip = skip.view(torch.uint8) if skip.dtype == torch.bool else skip
+        assert skip.is_contiguous() and skip.numel() == l2.shape[0]
+    L.check(lib.mmvid_mp_sample(_ptr(l2), l2.shape[0], n, float(noise_scale), _ptr(skip), _ptr(Y), _ptr(tok), int(seed),
+                                int(offset), _stream()), "mp_sample")
+
+
+def mp_keep(Y, pmask, I_tok, k, mask_id, seed, offset, beams=1):
+    """Keep-mask draw of one mask-predict iteration (dalle_bert.py:646-664): keep k not-preserved tokens per (sample, beam)
+    without replacement, proportional to Y.  Returns (keep bool [samples*beams, Ttot], ids_in int64 [samples*beams, Ttot])."""
+    lib = L.load()
+    _req(Y, torch.float32)
+    nb, Ttot = Y.shape
+    assert Y.is_contiguous() and I_tok.is_contiguous() and I_tok.dtype == torch.int64 and I_tok.shape == Y.shape
+    pm = None
+    if pmask is not None:
+        pm = pmask.reshape(-1)
+        pm = pm.view(torch.uint8) if pm.dtype == torch.bool else pm
+        assert pm.numel() == Ttot and pm.is_contiguous()
+    keep = torch.empty(nb * beams, Ttot, dtype=torch.uint8, device=Y.device)
+    ids_in = torch.empty(nb * beams, Ttot, dtype=torch.int64, device=Y.device)
+    L.check(lib.mmvid_mp_keep(_ptr(Y), _ptr(pm), _ptr(I_tok), nb, beams, Ttot, int(k), int(mask_id), _ptr(keep), _ptr(ids_in),
+                              int(seed), int(offset), _stream()), "mp_keep")
+    return keep.view(torch.bool), ids_in
+
+
 # ------------------------------------------------------------------------------------------------ attention
 
 def attention_fp32(qkv, B, S, H, mask_kind, prev_rows_dev):

@@ -219,6 +219,55 @@ def test_bert_batched_sampler_is_valid_and_seeded():
     assert im1.shape == (4, cfg["num_targets"], 3, cfg["image_size"], cfg["image_size"])
 
 
+@pytest.mark.parametrize("beams,dynamic", [(1, False), (1, True), (3, False), (2, True)])
+def test_device_resident_mask_predict_beams_and_dynamic_stop(beams, dynamic, monkeypatch):
+    """sampling_mode='batched' = the device-resident loop (fused draws, beam scoring / choice and dynamic stop on the device,
+    no host sync): valid ids, reproducible under torch.manual_seed, CUDA-graph replay == eager launches, and for beam 1
+    without dynamic stop statistically the same sampler as the torch-op loop (mean log-probability of the final ids under a
+    common scoring forward)."""
+    cfg = BERT_CASES["bert_tiny_nov"]
+    model, _ = build_bert(cfg, precision="tf32", sampling_mode="batched")
+    text = synth.synth_text(4, cfg["text_seq_len"], cfg["vocab"], 3).cuda()
+    mpc = dict(T1_n=10, T2_n=10, T3_n=30, N1_n=0.9, N2_n=0.1, N3_n=0.125, N4_n=0.0625, T1_t=10, T2_t=5, T3_t=35, N1_t=0.0,
+               N2_t=0.0, N3_t=0.0, N4_t=0.0, T=8, B=beams)
+    outs = {}
+    for sw in ("1", "0", "1"):
+        monkeypatch.setenv("MMVID_CUDA_GRAPH", sw)
+        torch.manual_seed(21)
+        im, _, s = model.generate_images(text, mask_predict_steps=8, dynamic=dynamic, mp_config=mpc)
+        assert s.min() >= 0 and s.max() < 1024 and im.shape[0] == 4
+        if sw in outs:
+            assert torch.equal(outs[sw], s)
+        outs[sw] = s
+    assert torch.equal(outs["0"], outs["1"])
+    torch.manual_seed(22)
+    _, _, s2 = model.generate_images(text, mask_predict_steps=8, dynamic=dynamic, mp_config=mpc)
+    assert not torch.equal(s2, outs["1"])
+    if beams == 1 and not dynamic:
+        # same sampler as the torch-op loop: compare how likely each loop's final ids are under the model itself
+        def mean_logp(seq):
+            control = model(text.repeat(seq.shape[0] // (4 * cfg["num_targets"]), 1), return_loss=False)
+            ids = seq.view(control.shape[0], -1)
+            x = torch.empty(control.shape[0], model.total_seq_len, cfg["dim"], device="cuda")
+            x[:, :control.shape[1]] = control
+            from mmvid_b200 import ops
+            ops.embed_gather(x, [model._target_segment(ids)])
+            hid = model.transformer_forward(x)
+            lg = model._head(hid[:, control.shape[1]:].reshape(-1, cfg["dim"]), model.to_logits).view(control.shape[0], -1, 1024)
+            return float(torch.log_softmax(lg, -1).gather(2, ids.unsqueeze(-1)).mean())
+        a, b = [], []
+        for rep in range(6):
+            monkeypatch.setenv("MMVID_SAMPLER", "device")
+            torch.manual_seed(100 + rep)
+            a.append(mean_logp(model.generate_images(text, mask_predict_steps=8, dynamic=False, mp_config=mpc)[2]))
+            monkeypatch.setenv("MMVID_SAMPLER", "torch")
+            torch.manual_seed(100 + rep)
+            b.append(mean_logp(model.generate_images(text, mask_predict_steps=8, dynamic=False, mp_config=mpc)[2]))
+        ma, mb = sum(a) / len(a), sum(b) / len(b)
+        print(f"mean log-prob of final ids: device sampler {ma:.4f}, torch-op sampler {mb:.4f}")
+        assert abs(ma - mb) < 0.15 * max(1.0, abs(mb))
+
+
 # ------------------------------------------------------------------------------------------------ ART-V
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 def test_artv_forward_logits_vs_reference_golden(prec):

@@ -502,3 +502,85 @@ def test_experimental_transposed_conv_tile_matches_fp64(monkeypatch, N, Cin, Cou
     monkeypatch.setenv("MMVID_CONV_SWAP", "1")
     assert relerr(ops.conv2d(xn, _pack(w), b, precision="tf32"), ref) < 1e-3
     assert relerr(ops.conv2d(xn, _pack(w), b, residual=res, precision="tf32"), ref + res) < 1e-3
+
+
+def test_mp_sample_draws_from_softmax_and_reports_the_drawn_probability():
+    """mmvid_mp_sample (fused softmax + categorical draw + gather, dalle_bert.py:527-534): Y is exactly the softmax
+    probability of the drawn token, the empirical distribution of 400 k draws of one row matches softmax (chi-square),
+    rows flagged in `skip` are untouched, the draw is a function of (seed, offset) only, and Gumbel noise at temperature T
+    changes the distribution the way the reference's formula says."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    n = 1024
+    base = (torch.randn(n, generator=g) * 2.0)
+    base[5] = 6.0
+    base[77] = -1e30  # zero-probability token
+    R = 400_000
+    logits = base.unsqueeze(0).repeat(R, 1).cuda().contiguous()
+    Y = torch.zeros(R, device="cuda")
+    tok = torch.full((R,), -1, dtype=torch.long, device="cuda")
+    ops.mp_sample(logits, Y, tok, seed=1234, offset=0)
+    p = torch.softmax(base.double(), 0)
+    assert int(tok.min()) >= 0 and int(tok.max()) < n and not bool((tok == 77).any())
+    assert torch.allclose(Y.cpu().double(), p[tok.cpu()], rtol=2e-5, atol=1e-9)
+    counts = torch.bincount(tok.cpu(), minlength=n).double()
+    big = p * R >= 20
+    chi2 = float((((counts - p * R) ** 2) / (p * R))[big].sum())
+    dof = int(big.sum()) - 1
+    assert chi2 < dof + 6 * (2 * dof) ** 0.5, (chi2, dof)
+    # determinism / seed sensitivity / skip
+    Y2, tok2 = torch.zeros_like(Y), torch.zeros_like(tok)
+    ops.mp_sample(logits, Y2, tok2, seed=1234, offset=0)
+    assert torch.equal(tok, tok2) and torch.equal(Y, Y2)
+    ops.mp_sample(logits, Y2, tok2, seed=1234, offset=1)
+    assert not torch.equal(tok, tok2)
+    skip = (torch.arange(R, device="cuda") % 3 == 0)
+    Y3, tok3 = torch.full_like(Y, -7.0), torch.full_like(tok, -7)
+    ops.mp_sample(logits, Y3, tok3, seed=99, offset=5, skip=skip)
+    assert bool((tok3[skip] == -7).all()) and bool((Y3[skip] == -7.0).all()) and int(tok3[~skip].min()) >= 0
+    # temperature: argmax of logits + T * gumbel follows softmax(logits / T); after the second softmax the draw is the
+    # reference's two-stage procedure - compare against a torch restatement by Monte Carlo on a small alphabet
+    small = torch.tensor([2.0, 1.0, 0.0, -1.0] + [-1e30] * 124).unsqueeze(0).repeat(200_000, 1).cuda().contiguous()
+    Ys, ts = torch.zeros(200_000, device="cuda"), torch.zeros(200_000, dtype=torch.long, device="cuda")
+    ops.mp_sample(small, Ys, ts, seed=7, offset=0, noise_scale=1.5)
+    U = torch.rand(200_000, 4, generator=g).cuda()
+    noisy = small[:, :4] + 1.5 * (-torch.log(-torch.log(U + 1e-20) + 1e-20))
+    ref_tok = torch.multinomial(torch.softmax(noisy, 1), 1)[:, 0]
+    f_ours = torch.bincount(ts.cpu(), minlength=4)[:4].double() / 200_000
+    f_ref = torch.bincount(ref_tok.cpu(), minlength=4)[:4].double() / 200_000
+    assert float((f_ours - f_ref).abs().max()) < 6e-3, (f_ours, f_ref)
+
+
+def test_mp_keep_is_sampling_without_replacement_proportional_to_y():
+    """mmvid_mp_keep (Gumbel-top-k): exactly k of the selectable tokens are kept (+ every preserved token), the next input
+    ids are kept-token-or-[MASK], beams draw independently, and the inclusion frequencies match those of
+    torch.multinomial(Y, k, replacement=False) (the call the reference makes, dalle_bert.py:651)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    Ttot, k, MASK = 96, 20, 1024
+    y = torch.rand(Ttot, generator=g) ** 3 + 1e-4
+    pm = torch.zeros(Ttot, dtype=torch.bool)
+    pm[:8] = True
+    trials = 20_000
+    Y = y.unsqueeze(0).repeat(trials, 1).cuda().contiguous()
+    I_tok = torch.randint(0, 1024, (trials, Ttot), generator=g).cuda()
+    keep, ids_in = ops.mp_keep(Y, pm.cuda(), I_tok, k, MASK, seed=5, offset=0)
+    assert keep.shape == (trials, Ttot) and keep.dtype == torch.bool
+    assert bool(keep[:, :8].all()) and bool((keep[:, 8:].sum(1) == k).all())
+    assert torch.equal(ids_in, torch.where(keep, I_tok, torch.full_like(I_tok, MASK)))
+    ref = torch.multinomial(Y[:, 8:], k, replacement=False)
+    ref_keep = torch.zeros(trials, Ttot - 8, dtype=torch.bool, device="cuda").scatter_(1, ref, True)
+    f_ours, f_ref = keep[:, 8:].float().mean(0), ref_keep.float().mean(0)
+    assert float((f_ours - f_ref).abs().max()) < 0.02, float((f_ours - f_ref).abs().max())
+    # beams: independent draws from the same Y; fewer selectable tokens than k: all of them are kept
+    keep2, _ = ops.mp_keep(Y[:4], pm.cuda(), I_tok[:4], k, MASK, seed=5, offset=1, beams=3)
+    assert keep2.shape == (12, Ttot) and bool((keep2[:, 8:].sum(1) == k).all()) and not torch.equal(keep2[0], keep2[1])
+    Yz = Y[:2].clone()
+    Yz[:, 30:] = 0.0
+    keep3, _ = ops.mp_keep(Yz, pm.cuda(), I_tok[:2], 40, MASK, seed=5, offset=2)
+    assert bool(keep3[:, 8:30].all()) and not bool(keep3[:, 30:].any())
+    # Shape-A sized rows (2048 tokens, k = 205 .. 1843)
+    Yb = torch.rand(4, 2048, generator=g).cuda()
+    for kk in (1, 205, 1843, 2048):
+        kp, _ = ops.mp_keep(Yb, None, torch.zeros(4, 2048, dtype=torch.long, device="cuda"), kk, MASK, seed=1, offset=kk)
+        assert bool((kp.sum(1) == kk).all())
