@@ -265,7 +265,7 @@ int mmvid_embed_backward(const float* dx, int B, int S, int D, const mmvid_embed
 int mmvid_transpose2d(const float* in, float* out, int R, int C, mmvid_stream_t stream);
 
 /* Profiling hook (not part of the data path): CTA (0,0) of every following mmvid_attention launch writes clock64()
- * stamps of its pipeline events into dev_buf (>= 512 uint64; NULL switches it off).  See scripts/att_trace.py. */
+ * stamps of its pipeline events into dev_buf (>= 1024 uint64; NULL switches it off).  See scripts/att_trace3.py. */
 int mmvid_debug_attention_trace(unsigned long long* dev_buf);
 
 /* ------------------------------------------------------------------------------------------------

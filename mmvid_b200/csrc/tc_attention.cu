@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[bi]);  // one arrival per warp (4 per group)
       if (tr) att3_stamp(a, tb + 5);
+      if (lane == 0 && j < 32) att3_stamp(a, 512 + (g * 4 + qd) * 32 + j);  // per-warp arrival (skew between the 4 warps)
       float rs0, rs1;
       unpack2(rs, rs0, rs1);
       l += rs0 + rs1;
@@ -544,9 +545,10 @@ static int mmvid_attention_v5(const CUtensorMap* tq, const CUtensorMap* tk, cons
 
 namespace mmvid { unsigned long long* g_att_trace = nullptr; }
 // Debug / profiling hook: CTA (0,0) of every following attention launch writes clock64() stamps of its pipeline events
-// into `dev_buf` (>= 512 entries; pass NULL to switch it off).  MMA threads: [2 n] = P(n) observed, [2 n + 1] = PV(n) /
+// into `dev_buf` (>= 1024 entries; pass NULL to switch it off).  MMA threads: [2 n] = P(n) observed, [2 n + 1] = PV(n) /
 // QK(n+3) issued, n = 2 j + g < 64; softmax warp 0 of tile g: [128 + g*192 + j*6 + {0: S ready, 1: S in registers,
-// 2: row max, 3: exps done / P stores issued, 4: P stores landed, 5: p_ready signalled}].
+// 2: row max, 3: exps done / P stores issued, 4: P stores landed, 5: p_ready signalled}]; every softmax warp (tile g,
+// lane quarter qd): [512 + (g*4 + qd)*32 + j] = its p_ready arrival at key step j < 32.
 extern "C" int mmvid_debug_attention_trace(unsigned long long* dev_buf) {
   mmvid::g_att_trace = dev_buf;
   return MMVID_OK;

@@ -22,7 +22,7 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
     import torch
     from mmvid_b200 import ops
     from mmvid_b200._lib import MASK_PREV, MASK_CAUSAL
-    odt = torch.float32 if prec == "tf32" else torch.bfloat16
+    odt = ops.act_dtype(prec)
     res = {"prec": prec, "impl": int(impl), "poly8": int(poly), "spin": int(spin), "dual": int(dual), "pp": int(pp)}
 
     def ref(qkv, B, S, H, kind, rows):
@@ -64,7 +64,7 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
     lib = L.load()
     B, S, H = 4, 2115, 12
     S_pad = (S + 127) // 128 * 128
-    dt = torch.float32 if prec == "tf32" else torch.bfloat16
+    dt = ops.act_dtype(prec)
     qkv = torch.randn(B * S, 3 * H * 64, device="cuda")
     q = torch.zeros(B, H, S_pad, 64, device="cuda", dtype=dt)
     k = torch.zeros_like(q)
@@ -95,7 +95,7 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
     res["us"] = round(ms * 1000, 1)
     res["tflops"] = round(4.0 * S * S * H * 64 * B / ms / 1e9, 1)
     if impl in ("2", "3", "4"):
-        buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+        buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
         L.check(lib.mmvid_debug_attention_trace(buf.data_ptr()))
         att()
         torch.cuda.synchronize()
@@ -112,8 +112,8 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         return one(*sys.argv[2:8])
-    variants = [("2", "0", "0", "0", "0"), ("3", "0", "0", "1", "0"), ("3", "2", "0", "1", "0"), ("4", "0", "0", "1", "0"), ("4", "2", "0", "1", "0")]
-    for prec in ("tf32", "bf16"):
+    variants = [("3", "0", "0", "1", "0"), ("3", "2", "0", "1", "0"), ("3", "4", "0", "1", "0"), ("3", "2", "0", "1", "1")]
+    for prec in ("tf32", "fp16", "bf16"):
         for impl, poly, spin, dual, pp in variants:
             try:
                 r = subprocess.run([sys.executable, __file__, "one", prec, impl, poly, spin, dual, pp], capture_output=True, text=True, timeout=100)

@@ -20,10 +20,10 @@ for fl in range(8):
     print(f"MMA {names[fl]:34s}: issue {t[0] / n:6.1f} clk/mma, total {t[1] / n:6.1f} clk/mma")
 B, S, H, D = 4, 2115, 12, 768
 qkv = torch.randn(B * S, 3 * D, device="cuda")
-odt = torch.float32 if prec == "tf32" else torch.bfloat16
+odt = ops.act_dtype(prec)
 for _ in range(2):
     ops.attention_tc(qkv, B, S, H, MASK_PREV, [65, 66], prec, out_dtype=odt)
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
 L.check(lib.mmvid_debug_attention_trace(buf.data_ptr()))
 ops.attention_tc(qkv, B, S, H, MASK_PREV, [65, 66], prec, out_dtype=odt)
 torch.cuda.synchronize()
@@ -34,8 +34,21 @@ print(f"{prec} impl 3 poly {os.environ.get('MMVID_ATT_POLY', '0')}: n = 2j+g; MM
 for n in range(0, 34):
     j, g = n >> 1, n & 1
     sm = [t[128 + g * 192 + j * 6 + i] - t0 for i in range(6)]
-    if n >= 30 or n < 6: print(f"n={n:2d} (j={j:2d} {'AB'[g]}) MMA seen {t[2 * n] - t0:6d} issued {t[2 * n + 1] - t0:6d} | softmax {sm}  busy {sm[5] - sm[0]}")
+    if n >= 28 or n < 8 or 14 <= n < 20: print(f"n={n:2d} (j={j:2d} {'AB'[g]}) MMA seen {t[2 * n] - t0:6d} issued {t[2 * n + 1] - t0:6d} | softmax {sm}  busy {sm[5] - sm[0]}")
 
+# arrival skew between the four warps of a softmax group (p_ready needs all four)
+for g in range(2):
+    for j in (6, 8, 10, 12):
+        arr = [t[512 + (g * 4 + qd) * 32 + j] - t0 for qd in range(4)]
+        print(f"tile {'AB'[g]} step {j}: p_ready arrivals of warps qd=0..3 {arr}  spread {max(arr) - min(arr)}; MMA saw it at {t[2 * (2 * j + g)] - t0}")
+# steady-state period and phase durations over the middle key steps
+for g in range(2):
+    rows = [[t[128 + g * 192 + j * 6 + i] for i in range(6)] for j in range(4, 14)]
+    per = [(rows[i + 1][0] - rows[i][0]) for i in range(len(rows) - 1)]
+    ph = [[r[i + 1] - r[i] for i in range(5)] for r in rows]
+    avg = [sum(p[i] for p in ph) / len(ph) for i in range(5)]
+    print(f"tile {'AB'[g]}: period {sum(per) / len(per):.0f} clk; phases ld {avg[0]:.0f} max {avg[1]:.0f} exp+st issue {avg[2]:.0f} st wait {avg[3]:.0f} signal {avg[4]:.0f}"
+          f" | wait for S {sum(rows[i + 1][0] - rows[i][5] for i in range(len(rows) - 1)) / (len(rows) - 1):.0f}")
 if os.environ.get("MMVID_ATT_IMPL") == "4":
     for g in range(2):
         for I in range(4):

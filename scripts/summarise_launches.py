@@ -19,16 +19,20 @@ for r in csv.DictReader(lines):
     rows.append((r["Kernel Name"], v))
 
 
+def _clean(name):
+    n = re.sub(r"^void ", "", name)
+    return n.replace("<unnamed>::", "").replace("(anonymous namespace)::", "").replace("mmvid::", "")
+
+
 def family(name):
-    n = re.sub(r"<.*", "", name)
-    n = re.sub(r"^void ", "", n)
-    n = n.split("(")[0]
-    n = n.replace("(anonymous namespace)::", "").replace("mmvid::", "")
-    return n
+    n = _clean(name)
+    n = re.sub(r"<.*", "", n)
+    return n.split("(")[0]
 
 
 def variant(name):
-    m = re.search(r"<(.*)>", name)
+    n = _clean(name).split("(")[0]
+    m = re.search(r"<(.*)>", n)
     return m.group(1) if m else ""
 
 
