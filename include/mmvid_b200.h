@@ -279,7 +279,9 @@ int mmvid_debug_attention_trace(unsigned long long* dev_buf);
  *     kept.  keep [samples*beams, Ttot] (uint8), ids_in = keep ? I_tok : mask_id.  Y, I_tok: [samples, Ttot].
  * ---------------------------------------------------------------------------------------------- */
 int mmvid_mp_sample(const float* logits, long long rows, int n, float noise_scale, const uint8_t* skip, float* Y,
-                    int64_t* tok, unsigned long long seed, unsigned long long offset, mmvid_stream_t stream);
+                    int64_t* tok, unsigned long long seed, unsigned long long offset,
+                    const int* step_dev /* optional device counter added to offset (CUDA-graph replays) */,
+                    mmvid_stream_t stream);
 int mmvid_mp_keep(const float* Y, const uint8_t* pmask, const int64_t* I_tok, int samples, int beams, int Ttot, int k,
                   long long mask_id, uint8_t* keep, int64_t* ids_in, unsigned long long seed, unsigned long long offset,
                   mmvid_stream_t stream);

@@ -101,7 +101,7 @@ SIGNATURES = {
     "mmvid_cross_entropy": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p]),
     "mmvid_embed_backward": (_i, [_p, _i, _i, _i, C.POINTER(EmbedSegment), _p, _p, _p, _p]),
     "mmvid_transpose2d": (_i, [_p, _p, _i, _i, _p]),
-    "mmvid_mp_sample": (_i, [_p, _ll, _i, _f, _p, _p, _p, C.c_ulonglong, C.c_ulonglong, _p]),
+    "mmvid_mp_sample": (_i, [_p, _ll, _i, _f, _p, _p, _p, C.c_ulonglong, C.c_ulonglong, _p, _p]),
     "mmvid_mp_keep": (_i, [_p, _p, _p, _i, _i, _i, _i, _ll, _p, _p, C.c_ulonglong, C.c_ulonglong, _p]),
     "mmvid_debug_attention_trace": (_i, [_p]),
     "mmvid_debug_decode_trace": (_i, [_p]),

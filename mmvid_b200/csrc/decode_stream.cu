@@ -72,6 +72,15 @@ __device__ __forceinline__ float h16_to_f32(uint32_t bits16, int f16) {
   if (f16) return __half2float(__ushort_as_half((unsigned short)bits16));
   return __uint_as_float(bits16 << 16);
 }
+template <bool F16>
+__device__ __forceinline__ void unpack2_t(uint32_t w, float& lo, float& hi) {
+  if constexpr (F16) {
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = v.x; hi = v.y;
+  } else {
+    lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ void unpack2_h16(uint32_t w, int f16, float& lo, float& hi) {
   if (f16) {
     const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
@@ -158,57 +167,111 @@ __device__ __forceinline__ void issue_slab(const StreamParams& p, int w, int n_w
 // The B activation rows are staged (LayerNorm-ed) in shared memory; items (column, K slice) are dealt round robin to the
 // 16 warps, each item loads its activation slice into registers, streams its weight slice from the ring slab and leaves
 // one partial per row in shared memory; the K slices of a column are then summed in a fixed order.
-template <int MAXB>
+template <int MAXB, bool F16>
 __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const float* __restrict__ A, long long lda, int K,
                            const float* ln_g, const float* ln_b, int N, const float* __restrict__ bias, int act,
                            const float* residual, float* out, long long ldo, bool qkv_mode, const StreamLayer* L, int pos,
                            float* sm_act, float* sm_part, int tphase, const uint64_t* slab_bar, uint32_t slab_par) {
   const int B = p.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ds_stamp(p, tphase, 0);
-  // ---- stage A [B, K] (fp32, written by other CTAs before the barrier: L2 loads)
-  for (int i = threadIdx.x; i < B * (K >> 2); i += DS_THREADS) {
-    const int b = i / (K >> 2), k4 = i - b * (K >> 2);
-    reinterpret_cast<float4*>(sm_act)[i] = ldcg_f4(A + b * lda + k4 * 4);
-  }
-  __syncthreads();
-  ds_stamp(p, tphase, 1);
-  if (ln_g != nullptr) {  // clip_model.py:188-193, eps 1e-5; two-pass statistics, one warp per row
-    for (int b = warp; b < B; b += DS_WARPS) {
-      float* x = sm_act + b * K;
-      float s = 0.f;
-      for (int c = lane; c < K; c += 32) s += x[c];
-      const float mean = warp_sum(s) / (float)K;
-      float qq = 0.f;
-      for (int c = lane; c < K; c += 32) { const float d = x[c] - mean; qq += d * d; }
-      const float rstd = rsqrtf(warp_sum(qq) / (float)K + 1e-5f);
-      for (int c = lane; c < K; c += 32) x[c] = (x[c] - mean) * rstd * __ldg(ln_g + c) + __ldg(ln_b + c);
-    }
-    __syncthreads();
-  }
-  ds_stamp(p, tphase, 2);
-  mbar_wait(const_cast<uint64_t*>(slab_bar), slab_par);  // this phase's weight slab has landed in the ring
-  ds_stamp(p, tphase, 3);
   int lo, hi;
   col_range(N, lo, hi);
   const int C = hi - lo;
+  // ---- everything the epilogue needs from global memory is requested NOW (one L2 round trip hidden behind the phase)
+  float bias_v = 0.f, res_v = 0.f;
+  if ((int)threadIdx.x < C * B) {
+    const int c = threadIdx.x / B, b = threadIdx.x - c * B;
+    if (bias) bias_v = __ldg(bias + lo + c);
+    if (residual) res_v = __ldcg(residual + b * ldo + lo + c);
+  }
+  // ---- stage A [B, K] (fp32, written by other CTAs before the barrier: L2 loads) into shared memory
+  if (ln_g != nullptr && K <= 1024) {
+    // LayerNorm (clip_model.py:188-193, eps 1e-5) while staging: one warp per row, the row lives in registers (two-pass
+    // statistics without touching memory twice); gamma / beta are requested before the row arrives
+    for (int b = warp; b < B; b += DS_WARPS) {
+      float4 x[8], gm[8], bt[8];
+      const int n4 = K >> 2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k4 = lane + 32 * i;
+        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gm[i] = x[i];
+        bt[i] = x[i];
+        if (k4 < n4) {
+          x[i] = ldcg_f4(A + b * lda + k4 * 4);
+          gm[i] = __ldg(reinterpret_cast<const float4*>(ln_g) + k4);
+          bt[i] = __ldg(reinterpret_cast<const float4*>(ln_b) + k4);
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+      const float mean = warp_sum(sum) / (float)K;
+      float qq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (lane + 32 * i < n4) {
+          const float a = x[i].x - mean, c2 = x[i].y - mean, d = x[i].z - mean, e2 = x[i].w - mean;
+          qq += (a * a + c2 * c2) + (d * d + e2 * e2);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(qq) / (float)K + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k4 = lane + 32 * i;
+        if (k4 < n4) {
+          float4 o;
+          o.x = (x[i].x - mean) * rstd * gm[i].x + bt[i].x;
+          o.y = (x[i].y - mean) * rstd * gm[i].y + bt[i].y;
+          o.z = (x[i].z - mean) * rstd * gm[i].z + bt[i].z;
+          o.w = (x[i].w - mean) * rstd * gm[i].w + bt[i].w;
+          reinterpret_cast<float4*>(sm_act + b * K)[k4] = o;
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < B * (K >> 2); i += DS_THREADS) {
+      const int b = i / (K >> 2), k4 = i - b * (K >> 2);
+      reinterpret_cast<float4*>(sm_act)[i] = ldcg_f4(A + b * lda + k4 * 4);
+    }
+    if (ln_g != nullptr) {  // rows longer than 1024: statistics from shared memory
+      __syncthreads();
+      for (int b = warp; b < B; b += DS_WARPS) {
+        float* x = sm_act + b * K;
+        float sum = 0.f;
+        for (int c = lane; c < K; c += 32) sum += x[c];
+        const float mean = warp_sum(sum) / (float)K;
+        float qq = 0.f;
+        for (int c = lane; c < K; c += 32) { const float d = x[c] - mean; qq += d * d; }
+        const float rstd = rsqrtf(warp_sum(qq) / (float)K + 1e-5f);
+        for (int c = lane; c < K; c += 32) x[c] = (x[c] - mean) * rstd * __ldg(ln_g + c) + __ldg(ln_b + c);
+      }
+    }
+  }
+  __syncthreads();
+  ds_stamp(p, tphase, 2);
+  mbar_wait(const_cast<uint64_t*>(slab_bar), slab_par);  // this phase's weight slab has landed in the ring
+  ds_stamp(p, tphase, 3);
   // K slices: MAXB x slice / 32 activation registers per lane (<= 96); more slices when the CTA has few columns
   const int slice_max = MAXB <= 4 ? 768 : 384;
   int KS = max(1, K / slice_max);
   while (C * KS < DS_WARPS && KS < 8 && (K / (KS * 2)) % 128 == 0) KS *= 2;
   const int slice = K / KS, gpl = slice >> 7;  // 4-element granules per lane (slice is a multiple of 128)
   const int items = C * KS;
+  int c = warp / KS, sl = warp - c * KS;  // item `warp`; the loop advances by DS_WARPS items without divisions
+  const int dc = DS_WARPS / KS, ds = DS_WARPS - dc * KS;
   for (int it = warp; it < items; it += DS_WARPS) {
-    const int c = it / KS, s = it - c * KS;
-    const int k0 = s * slice;
+    const int k0 = sl * slice;
     float acc[MAXB];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
     const uint2* wrow = reinterpret_cast<const uint2*>(slab + ((size_t)c * K + k0) * 2);
+#pragma unroll 2
     for (int g = 0; g < gpl; ++g) {
       const uint2 wv = wrow[g * 32 + lane];
       float w0, w1, w2, w3;
-      unpack2_h16(wv.x, p.f16, w0, w1);
-      unpack2_h16(wv.y, p.f16, w2, w3);
+      unpack2_t<F16>(wv.x, w0, w1);
+      unpack2_t<F16>(wv.y, w2, w3);
 #pragma unroll
       for (int b = 0; b < MAXB; ++b) {
         if (b < B) {
@@ -223,15 +286,17 @@ __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const flo
       const float v = warp_sum(acc[b]);
       if (lane == 0 && b < B) sm_part[it * MAXB + b] = v;
     }
+    c += dc; sl += ds;
+    if (sl >= KS) { sl -= KS; ++c; }
   }
   __syncthreads();
   ds_stamp(p, tphase, 4);
-  for (int i = threadIdx.x; i < C * B; i += DS_THREADS) {
-    const int c = i / B, b = i - c * B, n = lo + c;
+  if ((int)threadIdx.x < C * B) {  // C * B <= DS_THREADS (checked on the host)
+    const int cc0 = threadIdx.x / B, b = threadIdx.x - cc0 * B, n = lo + cc0;
     float v = 0.f;
-    for (int s = 0; s < KS; ++s) v += sm_part[(c * KS + s) * MAXB + b];
-    v = apply_act(v + (bias ? __ldg(bias + n) : 0.f), act);
-    if (residual) v += __ldcg(residual + b * ldo + n);
+    for (int s2 = 0; s2 < KS; ++s2) v += sm_part[(cc0 * KS + s2) * MAXB + b];
+    v = apply_act(v + bias_v, act);
+    if (residual) v += res_v;
     if (qkv_mode && n >= p.D) {  // K / V of the new token straight into the 16-bit caches [B, H, S_max, 64]
       const int cc = n - p.D, which = cc / p.D, c2 = cc - which * p.D, hh = c2 >> 6, d = c2 & 63;
       uint16_t* dst = (which == 0 ? L->kcache : L->vcache) + (((long long)b * p.H + hh) * p.S_max + pos) * 64 + d;
@@ -244,6 +309,7 @@ __device__ void gemv_phase(const StreamParams& p, const uint8_t* slab, const flo
 
 // Single-query attention over the 16-bit cache, split-KV over Z CTAs per (batch, head).  8 lanes x 16 bytes cover one
 // 64-dim row, so a warp load fetches 4 keys; 4 such loads (16 keys) of K and of V are in flight per warp.
+template <bool F16>
 __device__ void attention_phase(const StreamParams& p, const StreamLayer& L, int pos, int Z, float* sm_red) {
   const int B = p.B, H = p.H, len = pos + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -270,10 +336,11 @@ __device__ void attention_phase(const StreamParams& p, const StreamLayer& L, int
     float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = 0.f;
-    for (int s0 = w0; s0 < w1; s0 += 16) {
-      uint4 kk[4], vv[4];
+    // 32 keys per warp in flight: 8 K rows and 8 V rows per lane quartet are requested before the first one is used
+    for (int s0 = w0; s0 < w1; s0 += 32) {
+      uint4 kk[8], vv[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int su = s0 + u * 4 + kq;
         kk[u] = make_uint4(0, 0, 0, 0); vv[u] = make_uint4(0, 0, 0, 0);
         if (su < w1) {
@@ -281,13 +348,13 @@ __device__ void attention_phase(const StreamParams& p, const StreamLayer& L, int
           vv[u] = __ldcg(reinterpret_cast<const uint4*>(vb + (long long)su * 64 + dq * 8));
         }
       }
-      float sc[4];
+      float sc[8];
       float mx = m;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         float k0, k1, k2, k3, k4, k5, k6, k7;
-        unpack2_h16(kk[u].x, p.f16, k0, k1); unpack2_h16(kk[u].y, p.f16, k2, k3);
-        unpack2_h16(kk[u].z, p.f16, k4, k5); unpack2_h16(kk[u].w, p.f16, k6, k7);
+        unpack2_t<F16>(kk[u].x, k0, k1); unpack2_t<F16>(kk[u].y, k2, k3);
+        unpack2_t<F16>(kk[u].z, k4, k5); unpack2_t<F16>(kk[u].w, k6, k7);
         float d = qv[0] * k0 + qv[1] * k1 + qv[2] * k2 + qv[3] * k3 + qv[4] * k4 + qv[5] * k5 + qv[6] * k6 + qv[7] * k7;
         d += __shfl_xor_sync(0xffffffffu, d, 1);
         d += __shfl_xor_sync(0xffffffffu, d, 2);
@@ -301,12 +368,12 @@ __device__ void attention_phase(const StreamParams& p, const StreamLayer& L, int
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] *= alpha;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const float pu = (sc[u] == -INFINITY) ? 0.f : expf(sc[u] - mx);
           l += pu;
           float v0, v1, v2, v3, v4, v5, v6, v7;
-          unpack2_h16(vv[u].x, p.f16, v0, v1); unpack2_h16(vv[u].y, p.f16, v2, v3);
-          unpack2_h16(vv[u].z, p.f16, v4, v5); unpack2_h16(vv[u].w, p.f16, v6, v7);
+          unpack2_t<F16>(vv[u].x, v0, v1); unpack2_t<F16>(vv[u].y, v2, v3);
+          unpack2_t<F16>(vv[u].z, v4, v5); unpack2_t<F16>(vv[u].w, v6, v7);
           o[0] = fmaf(pu, v0, o[0]); o[1] = fmaf(pu, v1, o[1]); o[2] = fmaf(pu, v2, o[2]); o[3] = fmaf(pu, v3, o[3]);
           o[4] = fmaf(pu, v4, o[4]); o[5] = fmaf(pu, v5, o[5]); o[6] = fmaf(pu, v6, o[6]); o[7] = fmaf(pu, v7, o[7]);
         }
@@ -377,7 +444,7 @@ __device__ void attention_phase(const StreamParams& p, const StreamLayer& L, int
   }
 }
 
-template <int MAXB>
+template <int MAXB, bool F16>
 __global__ void __launch_bounds__(DS_THREADS, 1) artv_decode_stream_kernel(const __grid_constant__ StreamParams p) {
   // the step counter of a graph replay lives in device memory
   const int pos = p.pos + (p.pos_dev != nullptr ? __ldcg(p.pos_dev) : 0);
@@ -407,7 +474,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) artv_decode_stream_kernel(const
   auto gemv = [&](const float* A, long long lda, int K, const float* ln_g, const float* ln_b, int N, const float* bias, int act,
                   const float* residual, float* out, long long ldo, bool qkv_mode, const StreamLayer* L) {
     if (threadIdx.x == 0) { fence_proxy_async(); issue_slab(p, w + DS_SLOTS - 1, n_wphases, ring, full); }
-    gemv_phase<MAXB>(p, ring + (size_t)(w % DS_SLOTS) * p.slot_bytes, A, lda, K, ln_g, ln_b, N, bias, act, residual, out, ldo,
+    gemv_phase<MAXB, F16>(p, ring + (size_t)(w % DS_SLOTS) * p.slot_bytes, A, lda, K, ln_g, ln_b, N, bias, act, residual, out, ldo,
                      qkv_mode, L, pos, sm_act, sm_part, tp, &full[w % DS_SLOTS], (uint32_t)(w / DS_SLOTS) & 1u);
     ++w;
   };
@@ -422,7 +489,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) artv_decode_stream_kernel(const
     gemv(p.h, D, D, L.ln1_w, L.ln1_b, 3 * D, L.in_b, MMVID_ACT_NONE, nullptr, p.q, D, true, &L);  // q -> p.q, k / v -> caches
     barrier();
     ds_stamp(p, tp, 0);
-    attention_phase(p, L, pos, Z, sm_part);  // no weights: the ring keeps filling meanwhile
+    attention_phase<F16>(p, L, pos, Z, sm_part);  // no weights: the ring keeps filling meanwhile
     barrier();
     gemv(p.att, D, D, nullptr, nullptr, D, L.out_b, MMVID_ACT_NONE, p.h, p.h, D, false, &L);     // out-proj + residual
     barrier();
@@ -533,12 +600,15 @@ extern "C" int mmvid_artv_decode_stream(const mmvid_decode_layer16* layers, int 
   p.logits = logits; p.n_logits = n_logits;
   p.B = B; p.D = D; p.H = H; p.S_max = S_max; p.pos = pos; p.f16 = f16 ? 1 : 0; p.slot_bytes = (int)slot;
   p.trace = g_decode_trace;
-  static size_t smem_set[2] = {0, 0};
-  void* kern = maxb == 4 ? (void*)artv_decode_stream_kernel<4> : (void*)artv_decode_stream_kernel<8>;
-  if (smem > smem_set[maxb == 8]) {
+  static size_t smem_set[4] = {0, 0, 0, 0};
+  const int ki = (maxb == 8 ? 2 : 0) + (p.f16 ? 1 : 0);
+  void* kern = ki == 0 ? (void*)artv_decode_stream_kernel<4, false>
+               : ki == 1 ? (void*)artv_decode_stream_kernel<4, true>
+               : ki == 2 ? (void*)artv_decode_stream_kernel<8, false> : (void*)artv_decode_stream_kernel<8, true>;
+  if (smem > smem_set[ki]) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(artv_decode_stream): %s", cudaGetErrorString(err));
-    smem_set[maxb == 8] = smem;
+    smem_set[ki] = smem;
   }
   // Co-residency of the G = #SMs CTAs (1 per SM by shared memory) is what the grid barrier needs.  A cooperative launch
   // asserts it; under stream capture (the per-token CUDA graph of DALLE.generate_images) a plain launch is used: the

@@ -33,9 +33,11 @@ template <int MAXV>  // MAXV = n / 32 values per lane
 __global__ void __launch_bounds__(256) mp_sample_kernel(const float* __restrict__ logits, long long rows, int n,
                                                         float noise_scale, const uint8_t* __restrict__ skip,
                                                         float* __restrict__ Y, long long* __restrict__ tok,
-                                                        unsigned long long seed, unsigned long long offset) {
+                                                        unsigned long long seed, unsigned long long offset,
+                                                        const int* __restrict__ step_dev) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (step_dev != nullptr) offset += (unsigned long long)__ldg(step_dev);  // CUDA-graph replay: a fresh draw per replay
   if (skip != nullptr && skip[row]) return;
   const int lane = threadIdx.x & 31;
   const float4* src = reinterpret_cast<const float4*>(logits + row * n);
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(THREADS) mp_keep_kernel(const float* __restric
 
 extern "C" int mmvid_mp_sample(const float* logits, long long rows, int n, float noise_scale, const uint8_t* skip,
                                float* Y, int64_t* tok, unsigned long long seed, unsigned long long offset,
-                               mmvid_stream_t stream) {
+                               const int* step_dev, mmvid_stream_t stream) {
   MMVID_REQUIRE(n % 128 == 0 && n >= 128 && n <= 1024, "n: multiple of 128, <= 1024");
   if (rows == 0) return MMVID_OK;
   const int wpb = 8;
@@ -196,14 +198,14 @@ extern "C" int mmvid_mp_sample(const float* logits, long long rows, int n, float
   cudaStream_t st = to_stream(stream);
   long long* t = reinterpret_cast<long long*>(tok);
   switch (n / 32) {
-    case 32: mp_sample_kernel<32><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
-    case 28: mp_sample_kernel<28><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
-    case 24: mp_sample_kernel<24><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
-    case 20: mp_sample_kernel<20><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
-    case 16: mp_sample_kernel<16><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
-    case 12: mp_sample_kernel<12><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
-    case 8: mp_sample_kernel<8><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
-    default: mp_sample_kernel<4><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset); break;
+    case 32: mp_sample_kernel<32><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
+    case 28: mp_sample_kernel<28><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
+    case 24: mp_sample_kernel<24><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
+    case 20: mp_sample_kernel<20><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
+    case 16: mp_sample_kernel<16><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
+    case 12: mp_sample_kernel<12><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
+    case 8: mp_sample_kernel<8><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
+    default: mp_sample_kernel<4><<<grid, wpb * 32, 0, st>>>(logits, rows, n, noise_scale, skip, Y, t, seed, offset, step_dev); break;
   }
   return check_launch("mp_sample");
 }

@@ -748,6 +748,8 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
                                long long ldc, long long M, int N, int K, int act, int precision, cudaStream_t st) {
   const bool tf32 = precision == MMVID_TF32;
   MMVID_REQUIRE(precision == MMVID_TF32 || precision == MMVID_BF16 || precision == MMVID_F16, "precision");
+  if (act == MMVID_ACT_QUICKGELU && !tf32 && c_dtype != MMVID_DT_F32 && env_int("MMVID_GELU_TANH", 1))
+    act = MMVID_ACT_QUICKGELU_TANH;  // 16-bit result: one MUFU op per element instead of two (see common.cuh)
   const int want = tf32 ? MMVID_DT_F32 : (precision == MMVID_F16 ? MMVID_DT_F16 : MMVID_DT_BF16);
   MMVID_REQUIRE(a_dtype == want && w_dtype == want,
                 "operand dtype must match precision (fp32 for TF32, bf16 for BF16, fp16 for F16)");

@@ -361,13 +361,17 @@ class DALLE(nn.Module):
             h_buf = xt.view(B, D)
             inv_t = 1.0 / float(temperature)
 
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator (follows torch.manual_seed), no device sync
+            y_buf = torch.empty(B, device=dev, dtype=torch.float32)
+            tok_buf = torch.empty(B, device=dev, dtype=torch.long)
+
             def token_step():
                 lg = logits_buf * inv_t if temperature != 1.0 else logits_buf
-                probs = ops.softmax_logits(lg)
-                sample = torch.multinomial(probs, 1)
+                # fused softmax + categorical draw (csrc/sampling.cu); the Philox offset follows the device step counter
+                ops.mp_sample(lg, y_buf, tok_buf, seed, 0, step_dev=t_dev)
                 t_idx = t_dev.long()
-                out_tokens.scatter_(1, t_idx.view(1, 1).expand(B, 1), sample)
-                h_buf.copy_(emb_w[sample[:, 0]] + pos_table.index_select(0, t_idx))
+                out_tokens.scatter_(1, t_idx.view(1, 1).expand(B, 1), tok_buf.view(B, 1))
+                h_buf.copy_(emb_w[tok_buf] + pos_table.index_select(0, t_idx))
                 stream_step(h_buf, P, t_dev)
                 t_dev.add_(1)
 
@@ -391,7 +395,8 @@ class DALLE(nn.Module):
             L.add_launch_count(per_replay * (n_steps - 2))
             # the last token only needs the sampling half of the step
             lg = logits_buf * inv_t if temperature != 1.0 else logits_buf
-            out_tokens[:, n_steps - 1] = torch.multinomial(ops.softmax_logits(lg), 1)[:, 0]
+            ops.mp_sample(lg, y_buf, tok_buf, seed, 0, step_dev=t_dev)
+            out_tokens[:, n_steps - 1] = tok_buf
             n_steps_loop = 0
         else:
             n_steps_loop = n_steps

@@ -195,7 +195,7 @@ def softmax_logits(logits, noise=None, noise_scale=0.0):
     return probs.view_as(logits)
 
 
-def mp_sample(logits, Y, tok, seed, offset, noise_scale=0.0, skip=None):
+def mp_sample(logits, Y, tok, seed, offset, noise_scale=0.0, skip=None, step_dev=None):
     """Fused softmax + categorical draw + gather per row of `logits` [..., n] (dalle_bert.py:527-534); updates Y (float32)
     and tok (int64) of the rows whose `skip` flag (uint8 / bool) is not set."""
     lib = L.load()
@@ -208,7 +208,7 @@ def mp_sample(logits, Y, tok, seed, offset, noise_scale=0.0, skip=None):
         skip = skip.view(torch.uint8) if skip.dtype == torch.bool else skip
         assert skip.is_contiguous() and skip.numel() == l2.shape[0]
     L.check(lib.mmvid_mp_sample(_ptr(l2), l2.shape[0], n, float(noise_scale), _ptr(skip), _ptr(Y), _ptr(tok), int(seed),
-                                int(offset), _stream()), "mp_sample")
+                                int(offset), _ptr(step_dev), _stream()), "mp_sample")
 
 
 def mp_keep(Y, pmask, I_tok, k, mask_id, seed, offset, beams=1):
