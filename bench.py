@@ -393,12 +393,73 @@ def kernel_roofline(model, args, peaks, S, B):
     z = torch.randn(B * Ttot, 256, device=dev)
     cb = model.vae.model.quantize.embedding.weight.detach()
     ms = timeit(lambda: ops.vq_argmin(z, cb))
-    out["vq_argmin"] = gbs(B * Ttot * (256 * 4 + 8) + cb.numel() * 4, ms)
+    # distances are 2 x T x 1024 x 256 fp32 FLOP on the CUDA cores (bit-exact indices need fp32); bytes are negligible
+    out["vq_argmin"] = dict(ms=ms, tflops_fp32=2.0 * B * Ttot * cb.shape[0] * 256 / ms / 1e9, bound="fp32 FFMA",
+                            bytes=B * Ttot * (256 * 4 + 8) + cb.numel() * 4)
     gx = torch.randn(B * cfg["num_targets"], cfg["image_size"] // 2, cfg["image_size"] // 2, 128, device=dev)
     gw, gb_ = torch.ones(128, device=dev), torch.zeros(128, device=dev)
     ms = timeit(lambda: ops.groupnorm(gx, gw, gb_, swish=True, fast=True))
     out["groupnorm_swish"] = gbs(gx.numel() * 4 * 3, ms)  # statistics pass + apply pass read, one write (K11)
     return out
+
+
+def decode_roofline(args, peaks, B, S_max, pos):
+    """ART-V workload: the streaming decode kernel (decode_stream.cu) alone, one token of all B samples at cache length
+    `pos` (the mean length over the generation), random 16-bit weights of the benchmark architecture.  HBM roofline:
+    algorithmic bytes = every 16-bit weight once (12 layers x 12 D^2 + head) + the K/V cache rows read (2 x layers x B x
+    pos x D x 2 B); the weights alone (170 MB) exceed the 126 MB L2, so back-to-back launches are L2-cold for them."""
+    import ctypes as C
+    from mmvid_b200 import _lib as L, ops
+    lib = L.load()
+    dev = "cuda"
+    D, H, NL = DIM, DIM // 64, LAYERS
+    f16 = 0 if args.precision == "bf16" else 1
+    dt = torch.bfloat16 if args.precision == "bf16" else torch.float16
+    g = torch.Generator().manual_seed(0)
+
+    def r(*s):
+        return (torch.randn(*s, generator=g) * 0.02).to(dev)
+    layers16 = (L.DecodeLayer16 * NL)()
+    keep = []
+    for li in range(NL):
+        t = dict(ln1_w=torch.ones(D, device=dev), ln1_b=torch.zeros(D, device=dev), in_b=r(3 * D), out_b=r(D),
+                 ln2_w=torch.ones(D, device=dev), ln2_b=torch.zeros(D, device=dev), fc_b=r(4 * D), proj_b=r(D),
+                 in_w=r(3 * D, D).to(dt), out_w=r(D, D).to(dt), fc_w=r(4 * D, D).to(dt), proj_w=r(D, 4 * D).to(dt),
+                 kcache=r(B, H, S_max, 64).to(dt), vcache=r(B, H, S_max, 64).to(dt))
+        keep.append(t)
+        for k, v in t.items():
+            setattr(layers16[li], k, v.data_ptr())
+    ws = torch.zeros(int(lib.mmvid_artv_decode_stream_workspace_floats(B, D, H)), device=dev)
+    head_w, head_b = r(1024, D).to(dt), r(1024)
+    lnw, lnb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    logits = torch.empty(B, 1024, device=dev)
+    h = r(B, D) * 50
+    st = ops._stream()
+
+    def call():
+        L.check(lib.mmvid_artv_decode_stream(layers16, NL, ops._ptr(h), ops._ptr(ws), ops._ptr(lnw), ops._ptr(lnb),
+                                             ops._ptr(head_w), ops._ptr(head_b), ops._ptr(logits), 1024, B, D, H, S_max,
+                                             pos, None, f16, st))
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    w_bytes = (NL * 12 * D * D + 1024 * D) * 2
+    kv_bytes = 2 * NL * B * (pos + 1) * D * 2
+    nbytes = w_bytes + kv_bytes
+    gbs = nbytes / ms / 1e6
+    return {"bound": "hbm", "kernel": "artv_decode_stream", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": nbytes, "ms": ms, "cache_len": pos,
+            "peak_source": peaks["source"] + " copy bandwidth",
+            "note": "one launch = one token of all %d samples (12 layers + head); weights %.0f MB + K/V %.0f MB per launch; the "
+                    "step is a chain of 61 grid-wide phases, so it is latency- not byte-bound (DESIGN 2.4)" % (B, w_bytes / 1e6, kv_bytes / 1e6)}
 
 
 def parity_selfcheck(model, args, S, dev):
@@ -573,6 +634,9 @@ def run_ours(args):
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             pass
+        if args.workload == "artv" and args.precision != "fp32" and B <= 8:
+            prefix = 1 + cfg["text_seq_len"] + fmap * fmap
+            roof_artv = decode_roofline(args, peaks, B, prefix + tokens_per_sample, prefix + tokens_per_sample // 2)
         roof = {"bound": "tensor", "kernel": dom, "achieved": kr[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                 "frac": kr[dom]["tflops"] / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": (3 * B * (DIM // 64) * S * 64 + B * S * DIM) * (2 if args.precision in ("bf16", "fp16") else 4)
@@ -597,6 +661,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000.0 * t_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof,
         }
+        if args.workload == "artv" and args.precision != "fp32" and B <= 8:
+            out["roofline"] = roof_artv
         out["parity"] = parity_selfcheck(model, args, S, dev)
         out["precision"] = {"transformer": args.precision,
                             "vae_decoder": vae_precision(args)}
