@@ -5,6 +5,10 @@
 //          2: SS kind::f16  128x128x16                        3: TS kind::f16  128x64x16
 //          4: SS kind::tf32 128x256x8                         5: SS kind::f16  128x256x16
 //          6: attention pattern tf32: 16 x TS 128x64 then 8 x SS 128x128, repeated   7: same, kind::f16 (8 + 4)
+//          8: SS kind::f16 128x64x16 (Q K^T against a 64-key tile)
+//   flavor 16 + k (k = 0..3): MUFU.EX2 issue rate seen by ONE warp while 1 / 4 / 8 / 12 warps (k = 0: one warp alone,
+//          k = 1, 2, 3: k warps on every SM sub-partition) each run n_mma x 8 independent ex2.approx; dev_out[0] = clock64
+//          cycles of warp 0, dev_out[1] = of the last warp.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -40,6 +44,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int flavor, int n_mma,
         case 3: mma_ts<false>(tm + 384, tm + (i & 7) * 8, desc_advance(bd, kk), make_idesc<false>(128, 64), 1); break;
         case 4: mma_ss<true>(tm, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<true>(128, 256), 1); break;
         case 5: mma_ss<false>(tm, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<false>(128, 256), 1); break;
+        case 8: mma_ss<false>(tm, desc_advance(ad, kk), desc_advance(bd, kk), make_idesc<false>(128, 64), 1); break;
         case 6: {
           const int r = i % 24;
           if (r < 16) mma_ts<true>(tm + 384, tm + r * 8, desc_advance(bd, kk), make_idesc<true>(128, 64), 1);
@@ -66,10 +71,35 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int flavor, int n_mma,
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
+__global__ void __launch_bounds__(384, 1) mufu_rate_kernel(int n, unsigned long long* out, float seed) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = seed * (float)(threadIdx.x + i) * 1e-3f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < n; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += v[i];
+  if (acc == 123.456f) out[2] = 1;  // keep the chains alive
+  if (threadIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  if (threadIdx.x == blockDim.x - 32) out[1] = (unsigned long long)(t1 - t0);
+}
+
 }  // namespace
 
 extern "C" int mmvid_debug_mma_rate(int flavor, int n_mma, unsigned long long* dev_out, mmvid_stream_t stream) {
-  MMVID_REQUIRE(flavor >= 0 && flavor <= 7 && n_mma > 0 && dev_out != nullptr, "flavor 0..7");
+  MMVID_REQUIRE(((flavor >= 0 && flavor <= 8) || (flavor >= 16 && flavor <= 19)) && n_mma > 0 && dev_out != nullptr,
+                "flavor 0..8 or 16..19");
+  if (flavor >= 16) {
+    const int warps = flavor == 16 ? 1 : 4 * (flavor - 16);
+    mufu_rate_kernel<<<1, 32 * warps, 0, to_stream(stream)>>>(n_mma, dev_out, 0.37f);
+    return check_launch("mufu_rate");
+  }
   static bool attr_set = false;
   const int smem = 98304 + 1024 + 256;
   if (!attr_set) {

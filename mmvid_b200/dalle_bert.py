@@ -132,6 +132,7 @@ class BERT(nn.Module):
         self.to_logits_vid = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, 1))
         self.current_step = 0
         self.sampling_mode = kwargs.get("sampling_mode", "reference")
+        self.batch_train_passes = kwargs.get("batch_train_passes", True)  # positive + REL / VID negatives in one pass
         self._ids_cache = {}
 
     # ------------------------------------------------------------------------------------------ properties
@@ -432,12 +433,13 @@ class BERT(nn.Module):
         csl, Ttot = self.control_seq_len, self.target_seq_len
         tgt_masked = torch.where(mask1, target_ids, torch.full_like(target_ids, MASK))
         control, target_emb = self._embed_train(text, visual_ids, tgt_masked)
-        out = self._transformer_train(torch.cat((control, target_emb), dim=1))
-        logits = self._head_train(out[:, csl:].reshape(B * Ttot, D), self.to_logits)
-        loss_msm = cross_entropy_selected(logits, target_ids.reshape(-1), (~mask1).reshape(-1))
-        bce = F.binary_cross_entropy_with_logits
-        ones, zeros = torch.ones(B, device=dev), torch.zeros(B, device=dev)
-        denom = max(1.0, float(not_fully_masked.sum()))
+        # The positive pass and the REL / VID negatives share the transformer and (unless negvc shortens the control
+        # sequence) the sequence length: they run as ONE pass over a 2B / 3B batch (the reference runs
+        # three passes, dalle_bert.py:1037,1057,1101).  Samples are independent inside the transformer, so the losses
+        # and gradients are those of the separate passes.
+        passes = [torch.cat((control, target_emb), dim=1)]
+        i_rel = i_vid = None
+        out_neg_rel = None
         if rel:
             assert B >= 2 and B % 2 == 0, "REL needs an even batch (control sequences are swapped between halves)"
             if text_neg is not None:  # negvc: explicit negative text, no visual segment (dalle_bert.py:1047-1055)
@@ -445,21 +447,45 @@ class BERT(nn.Module):
             else:
                 perm = swap_perm if swap_perm is not None else torch.cat((torch.arange(B // 2, B), torch.arange(0, B // 2))).to(dev)
                 control_neg = control[perm]
-            out_neg = self._transformer_train(torch.cat((control_neg, target_emb), dim=1))
+            neg = torch.cat((control_neg, target_emb), dim=1)
+            if neg.shape[1] == passes[0].shape[1] and self.batch_train_passes:
+                i_rel = len(passes)
+                passes.append(neg)
+            else:
+                out_neg_rel = self._transformer_train(neg)
+        do_vid = vid and self.num_targets > 1
+        if do_vid:
+            warp_masked = torch.where(mask1, target_warp_ids, torch.full_like(target_warp_ids, MASK))
+            _, warp_emb = self._embed_train(text, visual_ids, warp_masked)
+            neg = torch.cat((control, warp_emb), dim=1)
+            if self.batch_train_passes:
+                i_vid = len(passes)
+                passes.append(neg)
+            else:
+                out_neg_vid = self._transformer_train(neg)
+        outs = self._transformer_train(torch.cat(passes, dim=0) if len(passes) > 1 else passes[0])
+        out = outs[:B]
+        if i_rel is not None:
+            out_neg_rel = outs[i_rel * B:(i_rel + 1) * B]
+        if i_vid is not None:
+            out_neg_vid = outs[i_vid * B:(i_vid + 1) * B]
+        logits = self._head_train(out[:, csl:].reshape(B * Ttot, D), self.to_logits)
+        loss_msm = cross_entropy_selected(logits, target_ids.reshape(-1), (~mask1).reshape(-1))
+        bce = F.binary_cross_entropy_with_logits
+        ones, zeros = torch.ones(B, device=dev), torch.zeros(B, device=dev)
+        denom = max(1.0, float(not_fully_masked.sum()))
+        if rel:
             lp = self._head_train(out[:, self.rel_tok_index], self.to_logits_rel).squeeze(-1)
-            ln = self._head_train(out_neg[:, self.rel_tok_index], self.to_logits_rel).squeeze(-1)
+            ln = self._head_train(out_neg_rel[:, self.rel_tok_index], self.to_logits_rel).squeeze(-1)
             if rel_no_fully_masked:
                 loss_rel = ((bce(lp, ones, reduction="none") + bce(ln, zeros, reduction="none")) * not_fully_masked).sum() / denom
             else:
                 loss_rel = bce(lp, ones) + bce(ln, zeros)
         else:
             loss_rel = torch.tensor(0.0, device=dev)
-        if vid and self.num_targets > 1:
-            warp_masked = torch.where(mask1, target_warp_ids, torch.full_like(target_warp_ids, MASK))
-            _, warp_emb = self._embed_train(text, visual_ids, warp_masked)
-            out_neg = self._transformer_train(torch.cat((control, warp_emb), dim=1))
+        if do_vid:
             lp = self._head_train(out[:, self.vid_tok_index], self.to_logits_vid)
-            ln = self._head_train(out_neg[:, self.vid_tok_index], self.to_logits_vid)
+            ln = self._head_train(out_neg_vid[:, self.vid_tok_index], self.to_logits_vid)
             o1, z1 = torch.ones(B, 1, device=dev), torch.zeros(B, 1, device=dev)
             if rel_no_fully_masked:
                 loss_vid = bce(lp, o1, reduction="none").sum() / denom + bce(ln, z1, reduction="none").sum() / denom

@@ -1,17 +1,23 @@
 """Timeline of CTA (0,0) of the rotating-score-buffer attention kernel (MMVID_ATT_IMPL=3) at the benchmark shape, plus the
 raw tcgen05.mma rates (mmvid_debug_mma_rate).  clock64 stamps relative to the first one."""
 import os, sys, ctypes as C
-os.environ.setdefault("MMVID_ATT_IMPL", "3")
+os.environ.setdefault("MMVID_ATT_IMPL", "6")
 import torch
 sys.path.insert(0, ".")
 from mmvid_b200 import _lib as L, ops
 from mmvid_b200._lib import MASK_PREV
 lib = L.load()
 prec = sys.argv[1] if len(sys.argv) > 1 else "tf32"
-out = torch.zeros(2, dtype=torch.int64, device="cuda")
+out = torch.zeros(4, dtype=torch.int64, device="cuda")
 names = ["SS tf32 128x128x8", "TS tf32 128x64x8", "SS f16 128x128x16", "TS f16 128x64x16", "SS tf32 128x256x8", "SS f16 128x256x16",
          "att pattern tf32 (16 TS + 8 SS)", "att pattern f16 (8 TS + 4 SS)"]
-for fl in range(8):
+names += ["SS f16 128x64x16"]
+for k, w in enumerate((1, 4, 8, 12)):
+    L.check(lib.mmvid_debug_mma_rate(16 + k, 2000, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    t = out.cpu().tolist()
+    print(f"MUFU.EX2 {w:2d} warps: {t[0] / 16000:.2f} clk per warp instruction (warp 0), {t[1] / 16000:.2f} (last warp)")
+for fl in range(9):
     n = 960
     for _ in range(2):
         L.check(lib.mmvid_debug_mma_rate(fl, n, out.data_ptr(), None))
@@ -30,7 +36,7 @@ torch.cuda.synchronize()
 L.check(lib.mmvid_debug_attention_trace(None))
 t = buf.cpu().tolist()
 t0 = min(x for x in t if x > 0)
-print(f"{prec} impl 3 poly {os.environ.get('MMVID_ATT_POLY', '0')}: n = 2j+g; MMA: P(n) seen, PV(n)+QK(n+3) issued | softmax g(n) step j: S ready, regs, max, exps, st landed, signalled")
+print(f"{prec} impl {os.environ['MMVID_ATT_IMPL']} poly {os.environ.get('MMVID_ATT_POLY', '0')}: n = 2j+g; MMA: P(n) seen, PV(n)+QK(n+3) issued | softmax g(n) step j: S ready, regs, max, exps, st landed, signalled")
 for n in range(0, 34):
     j, g = n >> 1, n & 1
     sm = [t[128 + g * 192 + j * 6 + i] - t0 for i in range(6)]
@@ -54,3 +60,8 @@ if os.environ.get("MMVID_ATT_IMPL") == "4":
         for I in range(4):
             v = [t[480 + g * 16 + I * 4 + i] - t0 if t[480 + g * 16 + I * 4 + i] else -1 for i in range(4)]
             print(f"item {I} tile {'AB'[g]}: start {v[0]} last P sent {v[1]} O complete {v[2]} stored {v[3]}")
+if os.environ.get("MMVID_ATT_IMPL") == "6":
+    for g in range(2):
+        for I in range(4):
+            v = [t[768 + g * 32 + I * 4 + i] - t0 if t[768 + g * 32 + I * 4 + i] else -1 for i in range(4)]
+            print(f"item {I} tile {'AB'[g]}: first S seen {v[0]} last P signalled {v[1]} O in registers {v[2]} store issued {v[3]}")

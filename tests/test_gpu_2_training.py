@@ -18,12 +18,16 @@ def _fp32_reference_math_with_grad():
         yield
 
 
+@pytest.mark.parametrize("batched", [True, False], ids=["one_pass_3B", "three_passes"])
 @pytest.mark.parametrize("prec,tol_loss,tol_grad", [("fp32", 2e-5, 2e-4), ("tf32", 2e-3, 2e-2)])
 @pytest.mark.parametrize("name", ["bert_tiny", "bert_tiny_nov"])
-def test_training_losses_and_gradients_match_oracle_autograd(name, prec, tol_loss, tol_grad):
+def test_training_losses_and_gradients_match_oracle_autograd(name, prec, tol_loss, tol_grad, batched):
+    """batched: the positive pass and the REL / VID negatives as ONE transformer pass over a 3B batch (default) vs the
+    reference's three passes (dalle_bert.py:1037,1057,1101) - both against the oracle's three-pass autograd."""
     from oracle import mmvid_oracle as O
     cfg = BERT_CASES[name]
     model, sd = build_bert(cfg, precision=prec)
+    model.batch_train_passes = batched
     model.train()
     spec = bert_spec(cfg)
     B = cfg["batch"]
