@@ -44,6 +44,29 @@ static inline cudaStream_t to_stream(mmvid_stream_t s) { return reinterpret_cast
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) for the kernels of the transformer forward --------------------------------
+// A kernel launched through launch_chained() may start - block scheduling, barrier / TMEM / tensor-map setup - while
+// its predecessor in the stream is still draining; it must execute chain_wait() before it touches global memory (reads
+// of the predecessor's results AND writes the predecessor may still read).  chain_release() lets the successor's
+// blocks be scheduled as soon as every block of this grid has started.  Inside a captured CUDA graph the edge becomes a
+// programmatic dependency.  MMVID_PDL=0 launches the same kernels with full stream serialisation (the device-side
+// instructions are then no-ops).
+__device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool chained_launch_enabled();  // MMVID_PDL, read once (common.cu)
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = chained_launch_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -9,6 +9,9 @@
 //   flavor 16 + k (k = 0..3): MUFU.EX2 issue rate seen by ONE warp while 1 / 4 / 8 / 12 warps (k = 0: one warp alone,
 //          k = 1, 2, 3: k warps on every SM sub-partition) each run n_mma x 8 independent ex2.approx; dev_out[0] = clock64
 //          cycles of warp 0, dev_out[1] = of the last warp.
+//   flavor 20 + k (k = 0..3), 4 warps (one per sub-partition), per iteration: k = 0: 8 x cvt.rn.satfinite.f16x2.f32;
+//          k = 1: 8 x ex2 + 4 x cvt (the softmax mix); k = 2: 8 x fma.rn.f32x2; k = 3: 8 x ex2 + 8 x fma.rn.f32x2 -
+//          which of these share an execution pipe (clock64 cycles of warp 0 for n_mma iterations).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -90,11 +93,54 @@ __global__ void __launch_bounds__(384, 1) mufu_rate_kernel(int n, unsigned long 
   if (threadIdx.x == blockDim.x - 32) out[1] = (unsigned long long)(t1 - t0);
 }
 
+__global__ void __launch_bounds__(128, 1) pipe_mix_kernel(int mode, int n, unsigned long long* out, float seed) {
+  float v[8];
+  unsigned long long w[8];
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = seed * (float)(threadIdx.x + i) * 1e-3f;
+    w[i] = (unsigned long long)__float_as_uint(v[i]) * 0x100000001ull;
+    pk[i] = 0;
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < n; ++it) {
+    if (mode == 0 || mode == 1) {
+      if (mode == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < (mode == 0 ? 8 : 4); ++i)
+        asm volatile("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(v[i]), "f"(v[(i + 1) & 7]));
+    } else {
+      if (mode == 3) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(w[i]));
+    }
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += v[i] + __uint_as_float(pk[i]) + __uint_as_float((uint32_t)w[i]);
+  if (acc == 123.456f) out[2] = 1;
+  if (threadIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  if (threadIdx.x == 96) out[1] = (unsigned long long)(t1 - t0);
+}
+
 }  // namespace
 
 extern "C" int mmvid_debug_mma_rate(int flavor, int n_mma, unsigned long long* dev_out, mmvid_stream_t stream) {
-  MMVID_REQUIRE(((flavor >= 0 && flavor <= 8) || (flavor >= 16 && flavor <= 19)) && n_mma > 0 && dev_out != nullptr,
-                "flavor 0..8 or 16..19");
+  MMVID_REQUIRE(((flavor >= 0 && flavor <= 8) || (flavor >= 16 && flavor <= 23)) && n_mma > 0 && dev_out != nullptr,
+                "flavor 0..8 or 16..23");
+  if (flavor >= 20) {
+    pipe_mix_kernel<<<1, 128, 0, to_stream(stream)>>>(flavor - 20, n_mma, dev_out, 0.37f);
+    return check_launch("pipe_mix");
+  }
   if (flavor >= 16) {
     const int warps = flavor == 16 ? 1 : 4 * (flavor - 16);
     mufu_rate_kernel<<<1, 32 * warps, 0, to_stream(stream)>>>(n_mma, dev_out, 0.37f);

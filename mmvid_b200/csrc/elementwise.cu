@@ -2,12 +2,21 @@
 // QKV split/transposes, GroupNorm+swish (K11), VQ argmin (K14), codebook gather (K15), layout helpers.
 // All are coalesced along the channel (innermost) dimension with 128-bit accesses where alignment allows.
 #include "common.cuh"
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include <type_traits>
 
 namespace mmvid {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+
+bool chained_launch_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("MMVID_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
 }  // namespace mmvid
 
 using namespace mmvid;
@@ -100,6 +109,8 @@ template <int VEC_PER_LANE, typename OutT>
 __global__ void layernorm_warp_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, OutT* __restrict__ out, long long rows, int D,
                                       float eps) {
+  chain_release();
+  chain_wait();  // x is the previous kernel's result
   const int warps_per_block = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -161,13 +172,16 @@ extern "C" int mmvid_layernorm(const float* x, long long ldx, const float* gamma
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div<long long>(rows, wpb));
   cudaStream_t st = to_stream(stream);
+  cudaError_t err;
   if (out_dtype == MMVID_DT_F32)
-    layernorm_warp_kernel<8, float><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (float*)out, rows, D, eps);
+    err = launch_chained(layernorm_warp_kernel<8, float>, grid, dim3(wpb * 32), 0, st, x, ldx, gamma, beta, (float*)out, rows, D, eps);
   else if (out_dtype == MMVID_DT_F16)
-    layernorm_warp_kernel<8, __half><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__half*)out, rows, D, eps);
+    err = launch_chained(layernorm_warp_kernel<8, __half>, grid, dim3(wpb * 32), 0, st, x, ldx, gamma, beta, (__half*)out, rows, D,
+                         eps);
   else
-    layernorm_warp_kernel<8, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__nv_bfloat16*)out, rows,
-                                                                      D, eps);
+    err = launch_chained(layernorm_warp_kernel<8, __nv_bfloat16>, grid, dim3(wpb * 32), 0, st, x, ldx, gamma, beta,
+                         (__nv_bfloat16*)out, rows, D, eps);
+  if (err != cudaSuccess) return fail(MMVID_ECUDA, "layernorm launch: %s", cudaGetErrorString(err));
   return check_launch("layernorm");
 }
 

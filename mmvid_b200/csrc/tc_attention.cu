@@ -27,7 +27,6 @@
 // interval), never a dense [S,S] tensor.
 #include "common.cuh"
 #include "tc_common.cuh"
-#include "tc_epilogue.cuh"
 
 #include <stdlib.h>
 
@@ -35,6 +34,11 @@ using namespace mmvid;
 using namespace mmvid::tc;
 
 namespace {
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && v[0]) ? atoi(v) : dflt;
+}
 
 constexpr int ATT3_THREADS = 384;
 constexpr int BQ = 128, BKV = 128, HD = 64;
@@ -105,8 +109,8 @@ struct Att3Args {
   int B, H, S, S_pad, mask_kind;
   int prev_rows[4]; int n_prev;
   int spin;  // 1: the MMA threads poll p_ready with test_wait instead of try_wait
-  int pingpong;  // 1: the two softmax groups alternate their exponential phases (token per SM sub-partition)
   int dual;  // 1: two MMA-issuing threads (warps 1 and 3), one per query tile; 0: warp 1 issues everything
+  int spec;  // 16-bit kinds: 1 = speculative exponentials (no row max in the common case), see the softmax warps
 };
 
 template <bool TRACE>
@@ -124,7 +128,8 @@ constexpr size_t att3_smem_bytes() {
 
 // F16 (16-bit kinds only): fp16 operands / P / 16-bit output instead of bf16 - the tf32 mantissa at the kind::f16 rate.
 // P <= 2^8 (lazy rescale) and softmax inputs of O(10) sit comfortably inside the fp16 range.
-template <bool TF32, int POLY8, bool F16, bool TRACE>
+// SPEC (16-bit kinds): speculative exponentials, see the softmax warps
+template <bool TF32, int POLY8, bool F16, bool TRACE, bool SPEC = false>
 __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                        const __grid_constant__ CUtensorMap tmK,
                                                                        const __grid_constant__ CUtensorMap tmV, Att3Args a) {
@@ -145,7 +150,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
   // of the last phase the group saw - indistinguishable for a parity wait.  Each of the two is at most one phase ahead.
   uint64_t* o_full = bars + 21;   // [2][2]
   uint64_t* all_done = bars + 25;
-  uint64_t* tok = bars + 26;      // [2][4] MUFU ping-pong token per query tile and SM sub-partition (see softmax warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 512 + 1023) & ~(uintptr_t)1023);
   constexpr int ESZ = TF32 ? 4 : 2;
@@ -174,7 +178,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
       mbar_init(&o_full[2 * i], 1); mbar_init(&o_full[2 * i + 1], 1);
     }
     for (int i = 0; i < 6; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
-    for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     mbar_init(all_done, a.dual ? 2 : 1);
     fence_barrier_init();
   }
@@ -183,6 +186,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  chain_release();
+  chain_wait();  // Q / K / V^T come from the previous kernel; everything above overlapped its tail
 
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
@@ -363,78 +368,90 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
             }
         }
       }
-      float mx0 = __uint_as_float(r[0][0]), mx1 = __uint_as_float(r[0][1]);
+      // exponentials of the whole row against reference `nmc` (= -m_ref c), P stored over S, returns the row sum
+      auto exp_and_store = [&](float nmc) -> float {
+        const f2_t c2 = pack2(c, c), nmc2 = pack2(nmc, nmc);
+        f2_t rs = pack2(0.f, 0.f);
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = (ch == 0 ? 2 : 0); i < 32; i += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
-          if (i + 3 < 32) mx1 = fmax3(mx1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
-        }
-      const float mx = fmaxf(mx0, mx1);
-      if (tr) stamp6<TRACE>(a.trace, tb + 2);
-      // move the reference only when needed (warp-uniform decision because TMEM ld/st are warp collectives)
-      const bool need = (mx != -INFINITY) && (m_ref == -INFINITY || (mx - m_ref) * c > RESCALE_THRESH);
-      float alpha = 1.f;
-      bool resc = false;
-      if (need) {
-        if (m_ref != -INFINITY) { alpha = ex2_approx((m_ref - mx) * c); resc = true; }  // else: O row and l are still ~0
-        m_ref = mx;
-      }
-      if (__any_sync(0xffffffffu, resc)) {
-        // rare path: O_g *= alpha in TMEM (alpha = 1 for rows that keep their reference).  PV of this tile's previous
-        // step must have retired; PV of this step is not issued before p_ready below.
-        // PV_g(j-1) must have retired before O is read-modify-written.  It commits to barrier (j-1) & 1 of this tile as that
-        // barrier's phase (j-1) >> 1.  s_full(n) observed => QK(n-3) retired => PV(n-6) = PV_g(j-3), issued earlier by the
-        // same thread, retired: the barrier has completed every phase before this one, and cannot be past it (PV_g(j+1)
-        // needs P of this very step), so the parity wait is unambiguous however long ago the group last looked.
-        mbar_wait(&o_full[2 * g + ((j - 1) & 1)], (uint32_t)((j - 1) >> 1) & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t t[32];
-          tmem_ld32(t_o + hf * 32, t);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-          tmem_st32(t_o + hf * 32, t);
-        }
-      }
-      l *= alpha;
-      const float nmc = (m_ref == -INFINITY) ? 0.f : -m_ref * c;
-      const f2_t c2 = pack2(c, c), nmc2 = pack2(nmc, nmc);
-      f2_t rs = pack2(0.f, 0.f);
-      // MUFU ping-pong: warp qd of tile A and warp qd of tile B sit on the same SM sub-partition and share its 4 ex2/clk.
-      // Left alone the two groups fall into lockstep (r1n timeline): both exponential phases run together at half
-      // speed, both P tiles reach the tensor pipe together, and MUFU then idles while the MMAs drain.  The token makes the
-      // phases alternate A, B, A, B ...: one group's ld / max / st / barrier traffic hides behind the other's ex2 stream,
-      // and P tiles arrive evenly spaced.
-      if (a.pingpong && !(g == 0 && j == 0)) mbar_wait(&tok[g * 4 + qd], (uint32_t)(g == 0 ? j - 1 : j) & 1);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a0, a1, e0, e1;
-          unpack2(fma2(pack2(__uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1])), c2, nmc2), a0, a1);
-          if (((i >> 1) & 3) < POLY8 / 2) {
-            exp2_poly2<TF32 ? 4 : 3>(a0, a1, e0, e1);  // FMA pipe
-          } else {
-            e0 = ex2_approx(a0); e1 = ex2_approx(a1);  // MUFU; exp2(-inf) = 0 for masked keys
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1, e0, e1;
+            unpack2(fma2(pack2(__uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1])), c2, nmc2), a0, a1);
+            if (((i >> 1) & 3) < POLY8 / 2) {
+              exp2_poly2<TF32 ? 4 : 3>(a0, a1, e0, e1);  // FMA pipe
+            } else {
+              e0 = ex2_approx(a0); e1 = ex2_approx(a1);  // MUFU; exp2(-inf) = 0 for masked keys
+            }
+            rs = add2(rs, pack2(e0, e1));
+            if constexpr (TF32) {
+              r[ch][i] = __float_as_uint(e0); r[ch][i + 1] = __float_as_uint(e1);
+            } else {
+              pk[i >> 1] = pack_h16<F16>(e0, e1);
+            }
           }
-          rs = add2(rs, pack2(e0, e1));
-          if constexpr (TF32) {
-            r[ch][i] = __float_as_uint(e0); r[ch][i + 1] = __float_as_uint(e1);
-          } else {
-            pk[i >> 1] = pack_h16<F16>(e0, e1);
+          if constexpr (TF32) tmem_st32(t_s + ch * 32, r[ch]);
+          else tmem_st16(t_s + ch * 16, pk);
+        }
+        float rs0, rs1;
+        unpack2(rs, rs0, rs1);
+        return rs0 + rs1;
+      };
+      // SPEC (16-bit kinds, where the score row survives in registers): from the second key tile on the exponentials are
+      // taken against the CURRENT reference straight away - no row maximum (98 FMNMX and a dependent phase of ~280 clk per
+      // step), no rescale test.  A row sum <= 2^12 proves that no P exceeded 2^12 (fp16-safe, O and l in fp32); otherwise
+      // (new maximum far above the reference, or a row whose reference is still -inf) the warp falls back to the exact path
+      // below, which moves the reference and recomputes the row.  Effective lazy-rescale threshold: between 2^8 and 2^12.
+      float rsum = 0.f;
+      bool exact = true;
+      if constexpr (SPEC && !TF32) {
+        if (j > 0) {
+          rsum = exp_and_store((m_ref == -INFINITY) ? 0.f : -m_ref * c);
+          exact = __any_sync(0xffffffffu, !(rsum <= 4096.f));
+        }
+      }
+      if (exact) {
+        float mx0 = __uint_as_float(r[0][0]), mx1 = __uint_as_float(r[0][1]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+          for (int i = (ch == 0 ? 2 : 0); i < 32; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
+            if (i + 3 < 32) mx1 = fmax3(mx1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+          }
+        const float mx = fmaxf(mx0, mx1);
+        if (tr) stamp6<TRACE>(a.trace, tb + 2);
+        // move the reference only when needed (warp-uniform decision because TMEM ld/st are warp collectives)
+        const bool need = (mx != -INFINITY) && (m_ref == -INFINITY || (mx - m_ref) * c > RESCALE_THRESH);
+        float alpha = 1.f;
+        bool resc = false;
+        if (need) {
+          if (m_ref != -INFINITY) { alpha = ex2_approx((m_ref - mx) * c); resc = true; }  // else: O row and l are still ~0
+          m_ref = mx;
+        }
+        if (__any_sync(0xffffffffu, resc)) {
+          // rare path: O_g *= alpha in TMEM (alpha = 1 for rows that keep their reference).
+          // PV_g(j-1) must have retired before O is read-modify-written.  It commits to barrier (j-1) & 1 of this tile as that
+          // barrier's phase (j-1) >> 1.  s_full(n) observed => QK(n-3) retired => PV(n-6) = PV_g(j-3), issued earlier by the
+          // same thread, retired: the barrier has completed every phase before this one, and cannot be past it (PV_g(j+1)
+          // needs P of this very step), so the parity wait is unambiguous however long ago the group last looked.
+          mbar_wait(&o_full[2 * g + ((j - 1) & 1)], (uint32_t)((j - 1) >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t t[32];
+            tmem_ld32(t_o + hf * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st32(t_o + hf * 32, t);
           }
         }
-        if constexpr (TF32) tmem_st32(t_s + ch * 32, r[ch]);
-        else tmem_st16(t_s + ch * 16, pk);
-      }
-      if (a.pingpong) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tok[(g ^ 1) * 4 + qd]);  // exponentials issued: the other tile's warp may go
+        l *= alpha;
+        // (speculative pass already stored this row against the same reference: nothing to redo unless a reference moved)
+        if (!(SPEC && !TF32) || j == 0 || __any_sync(0xffffffffu, need))
+          rsum = exp_and_store((m_ref == -INFINITY) ? 0.f : -m_ref * c);
       }
       if (tr) stamp6<TRACE>(a.trace, tb + 3);
       tmem_st_wait();
@@ -444,9 +461,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
       if (lane == 0) mbar_arrive(&p_ready[bi]);  // one arrival per warp (4 per group)
       if (tr) stamp6<TRACE>(a.trace, tb + 5);
       if (lane == 0 && j < 32) stamp6<TRACE>(a.trace, 512 + (g * 4 + qd) * 32 + j);  // per-warp arrival (skew between the 4 warps)
-      float rs0, rs1;
-      unpack2(rs, rs0, rs1);
-      l += rs0 + rs1;
+      l += rsum;
     }
     // every MMA of BOTH groups must have retired before K/V smem is recycled as the output staging area
     mbar_wait(all_done, 0);
@@ -504,17 +519,18 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc3_kernel(const __
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-template <bool TF32, int POLY8, bool F16, bool TRACE>
+template <bool TF32, int POLY8, bool F16, bool TRACE, bool SPEC = false>
 int launch_att3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Att3Args& a, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = att3_smem_bytes<TF32>();
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(attention_tc3_kernel<TF32, POLY8, F16, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(attention_tc3_kernel<TF32, POLY8, F16, TRACE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(attention_tc3): %s", cudaGetErrorString(err));
     attr_set = true;
   }
   dim3 grid((a.S_pad / BQ + 1) / 2, a.B * a.H);
-  attention_tc3_kernel<TF32, POLY8, F16, TRACE><<<grid, ATT3_THREADS, smem, st>>>(tq, tk, tv, a);
+  cudaError_t err = launch_chained(attention_tc3_kernel<TF32, POLY8, F16, TRACE, SPEC>, grid, dim3(ATT3_THREADS), smem, st, tq, tk, tv, a);
+  if (err != cudaSuccess) return fail(MMVID_ECUDA, "attention_tc3 launch: %s", cudaGetErrorString(err));
   return check_launch("attention_tc3");
 }
 
@@ -528,412 +544,12 @@ int launch_att3_poly(int poly8, const CUtensorMap& tq, const CUtensorMap& tk, co
     return launch_att3<TF32, DP, F16, true>(tq, tk, tv, a, st);
   }
   if (poly8 == 0) return launch_att3<TF32, 0, F16, false>(tq, tk, tv, a, st);
+  if constexpr (!TF32) {
+    if (poly8 == 2 && a.spec) return launch_att3<TF32, 2, F16, false, true>(tq, tk, tv, a, st);
+  }
   if (poly8 == 2) return launch_att3<TF32, 2, F16, false>(tq, tk, tv, a, st);
   if (poly8 == 4) return launch_att3<TF32, 4, F16, false>(tq, tk, tv, a, st);
   return fail(MMVID_EINVAL, "attention_tc3: poly8 must be 0, 2 or 4%s", "");
-}
-
-// =====================================================================================================================
-// v6 (16-bit kinds, 16-bit output): PERSISTENT CTAs, the two query tiles run as DECOUPLED streams.
-//
-// What the v5 timelines showed (profiles/r2_b_ncu_fp16.md): (1) with three rotating score buffers S(n+2) is only issued
-// after PV(n-1) of the OTHER tile, so two softmax groups that have fallen into lockstep - the stable state - wait
-// ~470 clk per step for the tensor pipe; (2) prologue, pipeline ramp, O read-out and tear-down are ~12 k clk of a CTA's
-// ~54 k clk life, three times per SM.
-//
-//   TMEM columns:  S_A [0,128)  S_B [128,256)  P_A [256,320)  P_B [320,384)  O_A [384,448)  O_B [448,512)
-//
-// P (16-bit, two keys per column) no longer overwrites S: a softmax warp frees S as soon as the score row sits in its
-// registers (s_free), so QK^T(t+1) of a tile is issued ~250 clk after S(t) became visible and is ready long before the
-// group needs it, independent of the other tile.  P(t+1) is only stored once PV(t) has retired (o_full, normally long
-// past by then).  Every barrier has ONE producer and ONE consumer that sees every phase: parity = step & 1.
-// A CTA walks (batch-head, query pair) items c, c + grid, ...; the K / V rings, the MMA issue streams and the softmax
-// groups run straight through item boundaries: the next item's Q is prefetched into a second buffer while the current
-// one runs, QK^T(0) of the next item is issued during the last softmax step, and the O read-out (tcgen05.ld, o_free,
-// scale, swizzled staging, ONE TMA bulk store per tile with rows >= S clipped by the tensor map) overlaps the other
-// tile's main loop and the next item's first MMAs.
-constexpr int A6_KST = 3, A6_VST = 3;       // K / V ring depth
-constexpr int A6_TILE = BQ * HD * 2;        // 16 KB: every 16-bit tile (Q, K, V^T, O staging)
-constexpr int A6_NTILES = 4 + A6_KST + A6_VST + 2;
-constexpr size_t A6_SMEM = (size_t)A6_NTILES * A6_TILE + 1024 + 512;
-__host__ __device__ constexpr int S6_COL(int g) { return g * 128; }
-__host__ __device__ constexpr int P6_COL(int g) { return 256 + g * 64; }
-
-struct Att6Args {
-  unsigned long long* trace;
-  int trace_ext;  // MMVID_ATT_TRACE_EXT=1: extra stamps at [1024, 4096) (the caller's buffer must hold 4096 entries)
-  int spin;       // MMVID_ATT_SPIN=1: poll with test_wait on the critical barriers
-  int B, H, S, S_pad, mask_kind;
-  int prev_rows[4]; int n_prev;
-  int n_pairs, n_items;
-};
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// TRACE: clock64 timeline stamps compiled in (debug hook only: even predicated off they cost ~10 % of a softmax warp's
-// issue time - R2UR / LDC of the trace pointer sit in the dependent chain, ncu source view of v5)
-template <int POLY8, bool F16, bool TRACE>
-__global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tc6_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                       const __grid_constant__ CUtensorMap tmK,
-                                                                       const __grid_constant__ CUtensorMap tmV,
-                                                                       const __grid_constant__ CUtensorMap tmO, Att6Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* q_full = bars + 0;     // [2 tiles][2 buffers]
-  uint64_t* k_full = bars + 4;     // [3]
-  uint64_t* k_empty = bars + 7;    // [3] count 2: QK^T of both tiles
-  uint64_t* v_full = bars + 10;    // [3]
-  uint64_t* v_empty = bars + 13;   // [3] count 2
-  uint64_t* s_full = bars + 16;    // [2] QK^T(t) of tile g landed in S_g
-  uint64_t* s_free = bars + 18;    // [2] count 4: S_g(t) sits in the softmax warps' registers
-  uint64_t* p_ready = bars + 20;   // [2] count 4: P_g(t) stored (and O_g rescaled if it had to be)
-  uint64_t* o_full = bars + 22;    // [2] PV(t) of tile g retired: P_g may be overwritten, O_g may be read / rescaled
-  uint64_t* o_free = bars + 24;    // [2] count 4: O_g of the finished item sits in registers
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 512 + 1023) & ~(uintptr_t)1023);
-  auto sQ = [&](int g, int buf) { return tiles + (g * 2 + buf) * A6_TILE; };
-  auto sK = [&](int st) { return tiles + (4 + st) * A6_TILE; };
-  auto sV = [&](int st) { return tiles + (4 + A6_KST + st) * A6_TILE; };
-  auto sO = [&](int g) { return tiles + (4 + A6_KST + A6_VST + g) * A6_TILE; };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_kv_full = (a.S + BKV - 1) / BKV;
-  // item -> (batch-head, first query row, key tiles); identical in every role
-  auto item_bh = [&](int item) { return item / a.n_pairs; };
-  auto item_q0 = [&](int item) { return (item % a.n_pairs) * (2 * BQ); };
-  auto item_nkv = [&](int item) {
-    return a.mask_kind == MMVID_MASK_CAUSAL ? min(n_kv_full, (item_q0(item) + 2 * BQ - 1) / BKV + 1) : n_kv_full;
-  };
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmO);
-    for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1);
-      mbar_init(&o_free[i], 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 0) {
-    // ------------------------------------------------------------------ K producer (ring runs through item boundaries)
-    if (elect_one()) {
-      uint32_t st = 0, ph = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-        const int bh = item_bh(item), n_kv = item_nkv(item);
-        for (int j = 0; j < n_kv; ++j) {
-          mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_expect_tx(&k_full[st], A6_TILE);
-          tma_load_2d(sK(st), &tmK, &k_full[st], 0, bh * a.S_pad + j * BKV);
-          if (++st == A6_KST) { st = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ V^T producer
-    if (elect_one()) {
-      uint32_t st = 0, ph = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-        const int bh = item_bh(item), n_kv = item_nkv(item);
-        for (int j = 0; j < n_kv; ++j) {
-          mbar_wait(&v_empty[st], ph ^ 1);
-          mbar_expect_tx(&v_full[st], A6_TILE);
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d(sV(st) + kb * (HD * 128), &tmV, &v_full[st], j * BKV + kb * 64, bh * HD);
-          if (++st == A6_VST) { st = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1 || warp == 3) {
-    // ------------------------------------------------------------------ MMA issuers: warp 1 = tile A, warp 3 = tile B
-    const int g = warp == 3 ? 1 : 0;
-    if (elect_one() && (int)blockIdx.x < a.n_items) {
-      constexpr uint32_t idesc_qk = make_idesc_h16(F16, BQ, BKV);
-      constexpr uint32_t idesc_pv = make_idesc_h16(F16, BQ, HD);
-      constexpr uint32_t TB16 = A6_TILE >> 4;
-      const uint64_t dQ0 = make_smem_desc_sw128(smem_u32(sQ(g, 0)));
-      const uint64_t dK0 = make_smem_desc_sw128(smem_u32(sK(0)));
-      const uint64_t dV0 = make_smem_desc_sw128(smem_u32(sV(0)));
-      const uint32_t t_s = tmem_base + S6_COL(g), t_p = tmem_base + P6_COL(g), t_o = tmem_base + O_COL_OF(g);
-      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-      auto load_q = [&](int item, int it) {
-        uint64_t* bar = &q_full[g * 2 + (it & 1)];
-        mbar_expect_tx(bar, A6_TILE);
-        tma_load_2d(sQ(g, it & 1), &tmQ, bar, 0, item_bh(item) * a.S_pad + item_q0(item) + g * BQ);
-      };
-      // ONE loop, one copy of each issue sequence: iteration `step` issues QK^T(step + 1) - the look-ahead, which only needs
-      // S_g to be free - and then PV(step).  (qi, qit, qj) walk the QK^T stream, (pi, pit, pj) the PV stream one step behind.
-      int qi = blockIdx.x, qit = 0, qj = 0, qn = item_nkv(qi);
-      int pi = qi, pit = 0, pj = 0, pn = qn;
-      load_q(qi, 0);
-      for (uint32_t t = 0;; ++t) {  // t = global step of the QK^T issued in this iteration; PV(t - 1) follows
-        if (qi < a.n_items) {
-          if (qj == 0) mbar_wait(&q_full[g * 2 + (qit & 1)], (uint32_t)(qit >> 1) & 1);
-          mbar_wait(&k_full[ks], kph);
-          if (t > 0) {  // the previous score row has left TMEM
-            if (a.spin) mbar_wait_spin(&s_free[g], (t - 1) & 1);
-            else mbar_wait(&s_free[g], (t - 1) & 1);
-          }
-          tc_fence_after();
-          const uint64_t qd = dQ0 + (uint64_t)((qit & 1) * TB16), kd = dK0 + (uint64_t)(ks * TB16);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_ss<false>(t_s, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_qk, kk != 0);
-          tc_commit(&k_empty[ks]);
-          tc_commit(&s_full[g]);
-          if (a.trace_ext && t < 64) stamp6<TRACE>(a.trace, 1024 + g * 256 + t * 4 + 0);
-          if (++ks == A6_KST) { ks = 0; kph ^= 1; }
-          // first QK^T of an item: every QK^T of the previous item has retired (s_free(t-1) above), so the other Q buffer
-          // is free for the item after this one
-          if (qj == 0 && qi + (int)gridDim.x < a.n_items) load_q(qi + gridDim.x, qit + 1);
-          if (++qj == qn) { qj = 0; qi += gridDim.x; ++qit; if (qi < a.n_items) qn = item_nkv(qi); }
-        }
-        if (t == 0) continue;
-        mbar_wait(&v_full[vs], vph);
-        if (pj == 0 && pit > 0) mbar_wait(&o_free[g], (uint32_t)(pit - 1) & 1);  // previous item's O has been read out
-        if (a.trace_ext && t <= 64) stamp6<TRACE>(a.trace, 1024 + g * 256 + (t - 1) * 4 + 1);
-        if (a.spin) mbar_wait_spin(&p_ready[g], (t - 1) & 1);
-        else mbar_wait(&p_ready[g], (t - 1) & 1);
-        tc_fence_after();
-        if (a.trace_ext && t <= 64) stamp6<TRACE>(a.trace, 1024 + g * 256 + (t - 1) * 4 + 2);
-        if (pit == 0 && pj < 32) stamp6<TRACE>(a.trace, (2 * pj + g) * 2);
-        const uint64_t vd = dV0 + (uint64_t)(vs * TB16);
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_ts<false>(t_o, t_p + kb * 32 + kk * 8, vd + (uint64_t)(kb * (HD * 128 / 16) + kk * 2), idesc_pv,
-                          (pj != 0 || (kb | kk) != 0) ? 1u : 0u);
-        tc_commit(&v_empty[vs]);
-        tc_commit(&o_full[g]);
-        if (++vs == A6_VST) { vs = 0; vph ^= 1; }
-        if (pit == 0 && pj < 32) stamp6<TRACE>(a.trace, (2 * pj + g) * 2 + 1);
-        if (a.trace_ext && t <= 64) stamp6<TRACE>(a.trace, 1024 + g * 256 + (t - 1) * 4 + 3);
-        if (++pj == pn) {
-          pj = 0; pi += gridDim.x; ++pit;
-          if (pi >= a.n_items) break;
-          pn = item_nkv(pi);
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax groups (warps 4-7: tile A, 8-11: tile B)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int g = (warp - 4) >> 2;
-    const int qd = warp & 3;
-    const int row_local = qd * 32 + lane;
-    const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const uint32_t t_s = t_row + S6_COL(g), t_p = t_row + P6_COL(g), t_o = t_row + O_COL_OF(g);
-    const float c = 0.125f * 1.4426950408889634f;
-    constexpr float RESCALE_THRESH = 8.f;
-    const uint32_t stage = smem_u32(sO(g));
-    uint32_t t = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
-      const int bh = item_bh(item), q0 = item_q0(item), n_kv = item_nkv(item);
-      const int b = bh / a.H, h = bh - b * a.H;
-      const int row = q0 + g * BQ + row_local;
-      int lo = 0, hi = a.S;
-      if (a.mask_kind == MMVID_MASK_CAUSAL) hi = min(a.S, row + 1);
-      else if (a.mask_kind == MMVID_MASK_PREV) {
-        for (int i = 0; i < a.n_prev; ++i) if (a.prev_rows[i] == row) lo = row;
-      }
-      float m_ref = -INFINITY, l = 0.f;
-      for (int j = 0; j < n_kv; ++j, ++t) {
-        const int kv0 = j * BKV;
-        const bool tile_full = __all_sync(0xffffffffu, (kv0 >= lo) && (kv0 + BKV <= hi));
-        if (a.trace_ext && qd == 0 && lane == 0 && t < 64) stamp6<TRACE>(a.trace, 2048 + g * 256 + t * 4 + 0);
-        if (a.spin) mbar_wait_spin(&s_full[g], t & 1);
-        else mbar_wait(&s_full[g], t & 1);
-        if (a.trace_ext && qd == 0 && lane == 0 && t < 64) stamp6<TRACE>(a.trace, 2048 + g * 256 + t * 4 + 1);
-        tc_fence_after();
-        const bool tr = (qd == 0 && lane == 0 && it == 0 && j < 32);
-        const int tb = 128 + g * 192 + j * 6;
-        if (tr) stamp6<TRACE>(a.trace, tb + 0);
-        if (qd == 0 && lane == 0 && j == 0 && it < 8) stamp6<TRACE>(a.trace, 768 + g * 32 + it * 4 + 0);
-        uint32_t r[4][32];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) tmem_ld32(t_s + ch * 32, r[ch]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[g]);  // QK^T(t+1) may overwrite S_g
-        if (a.trace_ext && lane == 0 && t < 64) stamp6<TRACE>(a.trace, 3072 + (g * 4 + qd) * 64 + t);
-        if (tr) stamp6<TRACE>(a.trace, tb + 1);
-        if (!tile_full) {
-          const int nvalid = hi - kv0;
-          const int nvalid0 = __shfl_sync(0xffffffffu, nvalid, 0);
-          const bool simple = __all_sync(0xffffffffu, lo <= kv0 && nvalid == nvalid0);
-          if (simple) {
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              if ((ch + 1) * 32 <= nvalid) continue;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (ch * 32 + i >= nvalid) r[ch][i] = 0xff800000u;
-            }
-          } else {
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int col = kv0 + ch * 32 + i;
-                if (!(col >= lo && col < hi)) r[ch][i] = 0xff800000u;
-              }
-          }
-        }
-        // four independent max chains (two gave a 280 clk dependent chain in the v5 trace)
-        float mx[4];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          mx[ch] = fmax3(__uint_as_float(r[ch][0]), __uint_as_float(r[ch][1]), __uint_as_float(r[ch][2]));
-          mx[ch] = fmaxf(mx[ch], __uint_as_float(r[ch][3]));
-#pragma unroll
-          for (int i = 4; i < 32; i += 2) mx[ch] = fmax3(mx[ch], __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
-        }
-        const float mxr = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        if (tr) stamp6<TRACE>(a.trace, tb + 2);
-        const bool need = (mxr != -INFINITY) && (m_ref == -INFINITY || (mxr - m_ref) * c > RESCALE_THRESH);
-        float alpha = 1.f;
-        bool resc = false;
-        if (need) {
-          if (m_ref != -INFINITY) { alpha = ex2_approx((m_ref - mxr) * c); resc = true; }
-          m_ref = mxr;
-        }
-        if (__any_sync(0xffffffffu, resc)) {
-          // rare: O_g *= alpha in TMEM.  resc implies j > 0: PV(t-1) of this tile must have retired (o_full phase t-1),
-          // and PV(t) is not issued before p_ready(t) below.
-          mbar_wait(&o_full[g], (t - 1) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t tt[32];
-            tmem_ld32(t_o + hf * 32, tt);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) tt[i] = __float_as_uint(__uint_as_float(tt[i]) * alpha);
-            tmem_st32(t_o + hf * 32, tt);
-          }
-        }
-        l *= alpha;
-        const float nmc = (m_ref == -INFINITY) ? 0.f : -m_ref * c;
-        const f2_t c2 = pack2(c, c), nmc2 = pack2(nmc, nmc);
-        f2_t rs = pack2(0.f, 0.f);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float a0, a1, e0, e1;
-            unpack2(fma2(pack2(__uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1])), c2, nmc2), a0, a1);
-            if (((i >> 1) & 3) < POLY8 / 2) {
-              exp2_poly2<3>(a0, a1, e0, e1);
-            } else {
-              e0 = ex2_approx(a0); e1 = ex2_approx(a1);
-            }
-            rs = add2(rs, pack2(e0, e1));
-            pk[i >> 1] = pack_h16<F16>(e0, e1);
-          }
-          if (ch == 0 && t > 0) {
-            // P_g is single-buffered: PV(t-1) must have read it.  Placed after the first chunk's exponentials: PV(t-1) was
-            // issued ~700 clk ago by then.
-            mbar_wait(&o_full[g], (t - 1) & 1);
-            tc_fence_after();
-          }
-          tmem_st16(t_p + ch * 16, pk);
-        }
-        if (tr) stamp6<TRACE>(a.trace, tb + 3);
-        tmem_st_wait();
-        if (tr) stamp6<TRACE>(a.trace, tb + 4);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[g]);
-        if (tr) stamp6<TRACE>(a.trace, tb + 5);
-        if (lane == 0 && it == 0 && j < 32) stamp6<TRACE>(a.trace, 512 + (g * 4 + qd) * 32 + j);
-        float rs0, rs1;
-        unpack2(rs, rs0, rs1);
-        l += rs0 + rs1;
-      }
-      // ---- read-out of this item's O_g: overlaps the other tile's main loop and this tile's next QK^T
-      const bool tri = qd == 0 && lane == 0 && it < 8;
-      if (tri) stamp6<TRACE>(a.trace, 768 + g * 32 + it * 4 + 1);
-      mbar_wait(&o_full[g], (t - 1) & 1);
-      tc_fence_after();
-      uint32_t o[2][32];
-      tmem_ld32(t_o, o[0]);
-      tmem_ld32(t_o + 32, o[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[g]);  // PV(0) of the next item may overwrite O_g
-      if (tri) stamp6<TRACE>(a.trace, 768 + g * 32 + it * 4 + 2);
-      const float inv = 1.f / l;
-      const int q_tile0 = q0 + g * BQ;
-      if (qd == 0 && lane == 0) tma_store_wait_read();  // the previous item's bulk store has finished reading the staging tile
-      named_bar_sync(1 + g, 128);
-      // SWIZZLE_128B staging: row = 128 bytes, 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
-      const uint32_t srow = stage + row_local * 128;
-#pragma unroll
-      for (int cch = 0; cch < 8; ++cch) {
-        const uint32_t* src = &o[cch >> 2][(cch & 3) * 8];
-        sts128_u32(srow + (((uint32_t)cch ^ ((uint32_t)row_local & 7u)) << 4),
-                   pack_h16<F16>(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv),
-                   pack_h16<F16>(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv),
-                   pack_h16<F16>(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv),
-                   pack_h16<F16>(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv));
-      }
-      fence_proxy_async();
-      named_bar_sync(1 + g, 128);
-      if (qd == 0 && lane == 0 && q_tile0 < a.S) tma_store_3d(&tmO, stage, h * HD, q_tile0, b);
-      if (tri) stamp6<TRACE>(a.trace, 768 + g * 32 + it * 4 + 3);
-    }
-    if (qd == 0 && lane == 0) tma_store_wait_all();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
-}
-
-template <int POLY8, bool F16, bool TRACE>
-int launch_att6(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, const Att6Args& a,
-                cudaStream_t st) {
-  static bool attr_set = false;
-  static int n_sm = 0;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(attention_tc6_kernel<POLY8, F16, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A6_SMEM);
-    if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(attention_tc6): %s", cudaGetErrorString(err));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
-  }
-  const int grid = a.n_items < n_sm ? a.n_items : n_sm;
-  attention_tc6_kernel<POLY8, F16, TRACE><<<grid, ATT3_THREADS, A6_SMEM, st>>>(tq, tk, tv, to, a);
-  return check_launch("attention_tc6");
-}
-
-template <bool F16>
-int launch_att6_poly(int poly8, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
-                     const Att6Args& a, cudaStream_t st) {
-  if (a.trace != nullptr) {  // timeline build: POLY8 = 2 only
-    if (poly8 != 2) return fail(MMVID_EINVAL, "attention_tc6: the trace build exists for poly8 = 2 only%s", "");
-    return launch_att6<2, F16, true>(tq, tk, tv, to, a, st);
-  }
-  if (poly8 == 0) return launch_att6<0, F16, false>(tq, tk, tv, to, a, st);
-  if (poly8 == 2) return launch_att6<2, F16, false>(tq, tk, tv, to, a, st);
-  if (poly8 == 4) return launch_att6<4, F16, false>(tq, tk, tv, to, a, st);
-  return fail(MMVID_EINVAL, "attention_tc6: poly8 must be 0, 2 or 4%s", "");
 }
 
 }  // namespace
@@ -944,12 +560,13 @@ int launch_att6_poly(int poly8, const CUtensorMap& tq, const CUtensorMap& tk, co
 static int mmvid_attention_v5(const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv, void* out,
                               int out_h16, long long ldo, int B, int H, int S, int S_pad, int mask_kind,
                               const int* host_prev_rows, int n_prev, int kind, int poly8, int spin, int dual,
-                              int pingpong, unsigned long long* trace, cudaStream_t st) {
+                              unsigned long long* trace, cudaStream_t st) {
   Att3Args a{};
   a.trace = trace;
   a.out = out; a.ldo = ldo; a.out_h16 = out_h16;
   a.B = B; a.H = H; a.S = S; a.S_pad = S_pad; a.mask_kind = mask_kind; a.n_prev = n_prev;
-  a.spin = spin; a.dual = dual; a.pingpong = pingpong;
+  a.spin = spin; a.dual = dual;
+  a.spec = env_int("MMVID_ATT_SPEC", 1);
   for (int i = 0; i < n_prev; ++i) a.prev_rows[i] = host_prev_rows[i];
   if (kind == MMVID_TF32) return launch_att3_poly<true, false>(poly8, *tq, *tk, *tv, a, st);
   if (kind == MMVID_F16) return launch_att3_poly<false, true>(poly8, *tq, *tk, *tv, a, st);
@@ -968,13 +585,6 @@ extern "C" int mmvid_debug_attention_trace(unsigned long long* dev_buf) {
   mmvid::g_att_trace = dev_buf;
   return MMVID_OK;
 }
-
-namespace {
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && v[0]) ? atoi(v) : dflt;
-}
-}  // namespace
 
 extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, void* out, int out_dtype, long long ldo,
                                int B, int H, int S, int S_pad, int mask_kind, const int* host_prev_rows, int n_prev,
@@ -1005,32 +615,12 @@ extern "C" int mmvid_attention(const void* q, const void* k, const void* vt, voi
     int rc = make_tensor_map(&tv, vt, dt, 2, dims, str, box);
     if (rc) return rc;
   }
-  // v6 (persistent, decoupled tile streams): 16-bit kinds with 16-bit output through a TMA bulk store.  Opt-in
-  // (MMVID_ATT_IMPL=6): measured 92.0 us against 90.3 us for v5 at the benchmark shape (gpurun r2r)
-  if (!tf32 && out_dtype == dt && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && env_int("MMVID_ATT_IMPL", 5) == 6) {
-    CUtensorMap to;
-    uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)S, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)ldo * 2, (uint64_t)S * ldo * 2};
-    uint32_t box[3] = {64, 128, 1};
-    int rc = make_tensor_map(&to, out, dt, 3, dims, str, box);
-    if (rc) return rc;
-    Att6Args a6{};
-    a6.trace = mmvid::g_att_trace;
-    a6.trace_ext = env_int("MMVID_ATT_TRACE_EXT", 0);
-    a6.spin = env_int("MMVID_ATT_SPIN", 0);
-    a6.B = B; a6.H = H; a6.S = S; a6.S_pad = S_pad; a6.mask_kind = mask_kind; a6.n_prev = n_prev;
-    for (int i = 0; i < n_prev; ++i) a6.prev_rows[i] = host_prev_rows[i];
-    a6.n_pairs = (S_pad / BQ + 1) / 2;
-    a6.n_items = B * H * a6.n_pairs;
-    const int poly = env_int("MMVID_ATT_POLY", 2);
-    return precision == MMVID_F16 ? launch_att6_poly<true>(poly, tq, tk, tv, to, a6, to_stream(stream))
-                                  : launch_att6_poly<false>(poly, tq, tk, tv, to, a6, to_stream(stream));
-  }
   // Measured default (gpurun r2r, trace-free builds): 2 of every 8 exponentials on the FMA pipe in every kind (tf32: 98.3 us
-  // against 102.4 us with all of them on MUFU).  MMVID_ATT_POLY (0|2|4 of every 8 exponentials on the FMA pipe), MMVID_ATT_PP (0|1 MUFU ping-pong
-  // token), MMVID_ATT_SPIN (0|1) and MMVID_ATT_DUAL (0|1: one or two MMA-issuing threads) are tuning switches.
+  // against 102.4 us with all of them on MUFU).  MMVID_ATT_POLY (0|2|4 of every 8 exponentials on the FMA pipe),
+  // MMVID_ATT_SPEC (0|1 speculative exponentials in the 16-bit kinds), MMVID_ATT_SPIN (0|1) and MMVID_ATT_DUAL (0|1: one or
+  // two MMA-issuing threads) are tuning switches.
   return mmvid_attention_v5(&tq, &tk, &tv, out, out_dtype != MMVID_DT_F32, ldo, B, H, S, S_pad, mask_kind, host_prev_rows,
                             n_prev, precision, env_int("MMVID_ATT_POLY", 2), env_int("MMVID_ATT_SPIN", 0),
-                            env_int("MMVID_ATT_DUAL", 1), env_int("MMVID_ATT_PP", 0), mmvid::g_att_trace,
+                            env_int("MMVID_ATT_DUAL", 1), mmvid::g_att_trace,
                             to_stream(stream));
 }

@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  chain_release();
+  chain_wait();  // operands / residual come from the previous kernel; the setup above overlapped its tail
 
   if (warp == 0) {
     if (elect_one()) {
@@ -623,7 +625,9 @@ int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(err));
     attr_set = true;
   }
-  gemm_tc_kernel<TF32, BN, CONV, SWAP, H16><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC1, e);
+  cudaError_t err = launch_chained(gemm_tc_kernel<TF32, BN, CONV, SWAP, H16>, dim3(grid), dim3(GEMM_THREADS), smem, st, tmA, tmB, tmC,
+                                   tmC1, e);
+  if (err != cudaSuccess) return fail(MMVID_ECUDA, "gemm_tc launch: %s", cudaGetErrorString(err));
   return check_launch("gemm_tc");
 }
 

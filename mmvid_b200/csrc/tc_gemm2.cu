@@ -152,6 +152,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  chain_release();
+  chain_wait();  // activations (and the residual) come from the previous kernel; the setup above overlapped its tail
 
   if (warp == 0) {
     if (elect_one()) {
@@ -431,7 +433,9 @@ int launch2k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     if (err != cudaSuccess) return fail(MMVID_ECUDA, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(err));
     attr_set = true;
   }
-  gemm_tc2_kernel<TF32, BN, H16><<<2 * clusters, G2_THREADS, smem, st>>>(tmA, tmB, tmC, tmQ, tmK, tmR, e);
+  cudaError_t err = launch_chained(gemm_tc2_kernel<TF32, BN, H16>, dim3(2 * clusters), dim3(G2_THREADS), smem, st, tmA, tmB, tmC, tmQ,
+                                   tmK, tmR, e);
+  if (err != cudaSuccess) return fail(MMVID_ECUDA, "gemm_tc2 launch: %s", cudaGetErrorString(err));
   return check_launch(what);
 }
 

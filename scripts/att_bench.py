@@ -3,7 +3,7 @@
     python scripts/att_bench.py            # all variants, one subprocess each (a trapped kernel cannot poison the rest)
     python scripts/att_bench.py one <prec> <impl> <poly8> <spin> <dual>
 
-Variants: MMVID_ATT_IMPL = 5 (v5: rotating score buffers, one CTA per query pair) | 6 (v6: persistent, decoupled tile streams; 16-bit kinds),
+Variants (argument order: prec impl poly spin dual spec; impl is kept for the log only):
 MMVID_ATT_POLY = 0|2|4 (of every 8 exponentials on the FMA pipe), MMVID_ATT_SPIN = 0|1, MMVID_ATT_DUAL = 0|1.
 """
 import json
@@ -15,15 +15,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def one(prec, impl, poly, spin, dual="1", pp="1"):
-    os.environ["MMVID_ATT_IMPL"], os.environ["MMVID_ATT_POLY"], os.environ["MMVID_ATT_SPIN"] = impl, poly, spin
+def one(prec, impl, poly, spin, dual="1", spec="1"):
+    os.environ["MMVID_ATT_POLY"], os.environ["MMVID_ATT_SPIN"] = poly, spin
     os.environ["MMVID_ATT_DUAL"] = dual
-    os.environ["MMVID_ATT_PP"] = pp
+    os.environ["MMVID_ATT_SPEC"] = spec
     import torch
     from mmvid_b200 import ops
     from mmvid_b200._lib import MASK_PREV, MASK_CAUSAL
     odt = ops.act_dtype(prec)
-    res = {"prec": prec, "impl": int(impl), "poly8": int(poly), "spin": int(spin), "dual": int(dual), "pp": int(pp)}
+    res = {"prec": prec, "impl": int(impl), "poly8": int(poly), "spin": int(spin), "dual": int(dual), "spec": int(spec)}
 
     def ref(qkv, B, S, H, kind, rows):
         q, k, v = qkv.view(B, S, 3, H, 64).double().unbind(2)
@@ -94,17 +94,14 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
     ms = sum(ts[:10]) / 10
     res["us"] = round(ms * 1000, 1)
     res["tflops"] = round(4.0 * S * S * H * 64 * B / ms / 1e9, 1)
-    if impl in ("5", "6") and poly == "2":  # the timeline build exists for the default poly8 only
+    if poly == "2" and (spec == "0" or prec == "tf32"):  # the timeline build: default poly8, exact-max path
         buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
         L.check(lib.mmvid_debug_attention_trace(buf.data_ptr()))
         att()
         torch.cuda.synchronize()
         L.check(lib.mmvid_debug_attention_trace(None))
         t = buf.cpu().tolist()
-        if impl in ("3", "4", "5", "6"):   # MMA rows: [2n] P(n) seen; steady-state period per key step = 2 tile-steps
-            res["period_clk"] = round((t[2 * 28] - t[2 * 8]) / 10.0)
-        else:
-            res["period_clk"] = round((t[14 * 4] - t[4 * 4]) / 10.0)
+        res["period_clk"] = round((t[2 * 28] - t[2 * 8]) / 10.0)  # MMA rows: [2n] P(n) seen; period per key step = 2 tile-steps
         res["trace_softmaxA_j8"] = [t[128 + 8 * 6 + i] - t[128 + 8 * 6] for i in range(6)]
     print("ATT " + json.dumps(res), flush=True)
 
@@ -112,10 +109,10 @@ def one(prec, impl, poly, spin, dual="1", pp="1"):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         return one(*sys.argv[2:8])
-    v5 = [("5", "0", "0", "1", "0"), ("5", "2", "0", "1", "0")]
-    v6 = [("6", "0", "0", "1", "0"), ("6", "2", "0", "1", "0"), ("6", "4", "0", "1", "0")]
     for prec in (sys.argv[1:] or ("tf32", "fp16", "bf16")):
-        for impl, poly, spin, dual, pp in (v5 if prec == "tf32" else v5[1:] + v6):
+        variants = [("5", "0", "0", "1", "0"), ("5", "2", "0", "1", "0")] if prec == "tf32" else \
+                   [("5", "2", "0", "1", "0"), ("5", "2", "0", "1", "1"), ("5", "0", "0", "1", "0"), ("5", "4", "0", "1", "0")]
+        for impl, poly, spin, dual, pp in variants:
             try:
                 r = subprocess.run([sys.executable, __file__, "one", prec, impl, poly, spin, dual, pp], capture_output=True, text=True, timeout=100)
                 lines = [l for l in r.stdout.splitlines() if l.startswith("ATT ")]

@@ -1,7 +1,7 @@
-"""Timeline of CTA (0,0) of the rotating-score-buffer attention kernel (MMVID_ATT_IMPL=3) at the benchmark shape, plus the
-raw tcgen05.mma rates (mmvid_debug_mma_rate).  clock64 stamps relative to the first one."""
+"""Timeline of CTA (0,0) of the attention kernel at the benchmark shape (the TRACE build: default POLY8, exact-max path), plus the
+raw tcgen05.mma / MUFU / conversion / packed-FMA rates (mmvid_debug_mma_rate).  clock64 stamps relative to the first one."""
 import os, sys, ctypes as C
-os.environ.setdefault("MMVID_ATT_IMPL", "6")
+os.environ.setdefault("MMVID_ATT_POLY", "2")
 import torch
 sys.path.insert(0, ".")
 from mmvid_b200 import _lib as L, ops
@@ -17,6 +17,11 @@ for k, w in enumerate((1, 4, 8, 12)):
     torch.cuda.synchronize()
     t = out.cpu().tolist()
     print(f"MUFU.EX2 {w:2d} warps: {t[0] / 16000:.2f} clk per warp instruction (warp 0), {t[1] / 16000:.2f} (last warp)")
+for k, (nm, per) in enumerate((("8 x cvt.f16x2", 8), ("8 x ex2 + 4 x cvt.f16x2", 12), ("8 x fma.f32x2", 8), ("8 x ex2 + 8 x fma.f32x2", 16))):
+    L.check(lib.mmvid_debug_mma_rate(20 + k, 2000, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    t = out.cpu().tolist()
+    print(f"PIPE {nm:26s}: {t[0] / 2000:.1f} clk per iteration = {t[0] / 2000 / per:.2f} clk per warp instruction (one warp per sub-partition)")
 for fl in range(9):
     n = 960
     for _ in range(2):
@@ -36,7 +41,7 @@ torch.cuda.synchronize()
 L.check(lib.mmvid_debug_attention_trace(None))
 t = buf.cpu().tolist()
 t0 = min(x for x in t if x > 0)
-print(f"{prec} impl {os.environ['MMVID_ATT_IMPL']} poly {os.environ.get('MMVID_ATT_POLY', '0')}: n = 2j+g; MMA: P(n) seen, PV(n)+QK(n+3) issued | softmax g(n) step j: S ready, regs, max, exps, st landed, signalled")
+print(f"{prec} poly {os.environ.get('MMVID_ATT_POLY', '2')}: n = 2j+g; MMA: P(n) seen, PV(n)+QK(n+3) issued | softmax g(n) step j: S ready, regs, max, exps, st landed, signalled")
 for n in range(0, 34):
     j, g = n >> 1, n & 1
     sm = [t[128 + g * 192 + j * 6 + i] - t0 for i in range(6)]
@@ -55,13 +60,3 @@ for g in range(2):
     avg = [sum(p[i] for p in ph) / len(ph) for i in range(5)]
     print(f"tile {'AB'[g]}: period {sum(per) / len(per):.0f} clk; phases ld {avg[0]:.0f} max {avg[1]:.0f} exp+st issue {avg[2]:.0f} st wait {avg[3]:.0f} signal {avg[4]:.0f}"
           f" | wait for S {sum(rows[i + 1][0] - rows[i][5] for i in range(len(rows) - 1)) / (len(rows) - 1):.0f}")
-if os.environ.get("MMVID_ATT_IMPL") == "4":
-    for g in range(2):
-        for I in range(4):
-            v = [t[480 + g * 16 + I * 4 + i] - t0 if t[480 + g * 16 + I * 4 + i] else -1 for i in range(4)]
-            print(f"item {I} tile {'AB'[g]}: start {v[0]} last P sent {v[1]} O complete {v[2]} stored {v[3]}")
-if os.environ.get("MMVID_ATT_IMPL") == "6":
-    for g in range(2):
-        for I in range(4):
-            v = [t[768 + g * 32 + I * 4 + i] - t0 if t[768 + g * 32 + I * 4 + i] else -1 for i in range(4)]
-            print(f"item {I} tile {'AB'[g]}: first S seen {v[0]} last P signalled {v[1]} O in registers {v[2]} store issued {v[3]}")

@@ -471,6 +471,37 @@ def test_attention_fma_pipe_exponentials_agree_with_fp64(monkeypatch, prec, poly
         assert relerr(out, ref) < TOL[prec] * (1.5 if prec == "fp16" else 1), f"{prec} poly {poly} {kind}"
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("spec", ["0", "1"])
+def test_attention_speculative_exponentials_match_the_exact_max_path(monkeypatch, prec, spec):
+    """MMVID_ATT_SPEC=1 (default in the 16-bit kinds): exponentials against the current reference without a row maximum,
+    exact path only when a row sum exceeds 2^12.  Checked against fp64 on (a) ordinary scores, (b) scores whose maximum
+    climbs tile after tile (the fallback fires on most steps), (c) rows that are fully masked in their first key tiles
+    (mask_prev rows deep in the sequence: reference still -inf when the speculative pass runs), (d) a causal item."""
+    ops = _ops()
+    from oracle import mmvid_oracle as O
+    monkeypatch.setenv("MMVID_ATT_SPEC", spec)
+    odt = H16[prec]
+    tol = TOL[prec] * (1.5 if prec == "fp16" else 1)
+    B, S, H = 2, 900, 3
+    g = torch.Generator().manual_seed(17)
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g)
+    cases = [("plain", qkv.clone(), "mask_prev", (300, 301)), ("late_rows", qkv.clone(), "mask_prev", (700, 701)),
+             ("causal", qkv.clone(), "causal", ())]
+    ramp = qkv.clone()
+    ramp[:, H * 64:2 * H * 64] *= torch.linspace(0.3, 5.0, S).repeat(B).unsqueeze(1)
+    ramp[:, :H * 64] *= 2.0
+    cases.append(("climbing_max", ramp, "mask_prev", (300, 301)))
+    for name, x, kind, rows in cases:
+        x = x.cuda()
+        mask = O.build_attention_mask(S, kind, rows) if kind == "mask_prev" else O.build_attention_mask(S, "causal")
+        ref = _attn_ref(x, B, S, H, mask)
+        out = ops.attention_tc(x, B, S, H, ops.MASK_PREV if kind == "mask_prev" else ops.MASK_CAUSAL, rows, prec, out_dtype=odt).float()
+        assert torch.isfinite(out).all(), name
+        e = relerr(out, ref)
+        assert e < tol * (3 if name == "climbing_max" else 1), f"{prec} spec={spec} {name}: {e}"
+
+
 def test_groupnorm_streaming_kernel_exact_and_fast_swish():
     """groupnorm_apply2 (one channel quad per thread) for every VQGAN width, exact (expf / IEEE division) and MUFU swish."""
     ops = _ops()
