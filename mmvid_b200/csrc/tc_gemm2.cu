@@ -223,6 +223,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     const uint32_t st_row = st_base + (uint32_t)(lane * 128);
     if (lane == 0) { prefetch_tmap(&tmC); prefetch_tmap(&tmQ); prefetch_tmap(&tmV); }
     uint32_t tile_iter = 0, res_ph = 0;
+    float bias_nx0 = 0.f, bias_nx1 = 0.f;  // this lane's bias columns of the NEXT tile's two chunks
+    if (H16 && cluster_id < total_tiles) {
+      const int ng = (cluster_id % e.num_n_tiles) * BN + ch0 * 32 + lane;
+      bias_nx0 = (e.bias && ng < e.N) ? __ldg(e.bias + ng) : 0.f;
+      bias_nx1 = (e.bias && nch > 1 && ng + 32 < e.N) ? __ldg(e.bias + ng + 32) : 0.f;
+    }
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
       const int nt = tile % e.num_n_tiles, mt = tile / e.num_n_tiles;
       const int m0 = mt * (2 * BM) + (int)rank * BM;
@@ -242,6 +248,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         tma_store_wait_read();  // the buffer's previous bulk store has been read out
         mbar_expect_tx(&res_bar[ew], 4096);
         tma_load_2d(epi_stage + ew * 1024, &tmV, &res_bar[ew], n_grp0, m0 + q * 32);
+      }
+      // Bias: lane i keeps column i of each of the warp's two chunks (fetched ONE TILE AHEAD, see below) and the row owners
+      // pick the values up by shuffle.  Beside 227 KB of shared memory only ~1 KB of L1 is left, so a __ldg behind
+      // tcgen05.wait::ld was an exposed L2 round trip of ~800 clk per chunk.
+      float bias_c0 = 0.f, bias_c1 = 0.f;
+      if constexpr (H16) {
+        bias_c0 = bias_nx0; bias_c1 = bias_nx1;
+        const int tile_n = tile + num_clusters;
+        if (tile_n < total_tiles) {
+          const int ng = (tile_n % e.num_n_tiles) * BN + ch0 * 32 + lane;
+          bias_nx0 = (e.bias && ng < e.N) ? __ldg(e.bias + ng) : 0.f;
+          bias_nx1 = (e.bias && nch > 1 && ng + 32 < e.N) ? __ldg(e.bias + ng + 32) : 0.f;
+        }
       }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
@@ -273,14 +292,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         if (cc >= nvalid) continue;  // columns beyond N (warp-uniform)
         const int ncol = n_grp0 + cc * 32;
         float o[32];
+        if constexpr (H16) {
+          const float bias_l = cc == 0 ? bias_c0 : bias_c1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + 4 * i));
-          o[4 * i + 0] = __uint_as_float(racc[4 * i + 0]) + b.x;
-          o[4 * i + 1] = __uint_as_float(racc[4 * i + 1]) + b.y;
-          o[4 * i + 2] = __uint_as_float(racc[4 * i + 2]) + b.z;
-          o[4 * i + 3] = __uint_as_float(racc[4 * i + 3]) + b.w;
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(racc[i]) + __shfl_sync(0xffffffffu, bias_l, i);
+        } else {  // fp32 results: these GEMMs are not epilogue-bound and have no registers to spare - plain loads
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + 4 * i));
+            o[4 * i + 0] = __uint_as_float(racc[4 * i + 0]) + b.x;
+            o[4 * i + 1] = __uint_as_float(racc[4 * i + 1]) + b.y;
+            o[4 * i + 2] = __uint_as_float(racc[4 * i + 2]) + b.z;
+            o[4 * i + 3] = __uint_as_float(racc[4 * i + 3]) + b.w;
+          }
         }
         if (e.act != MMVID_ACT_NONE) {
 #pragma unroll
