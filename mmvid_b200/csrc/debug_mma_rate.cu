@@ -12,6 +12,7 @@
 //   flavor 20 + k (k = 0..3), 4 warps (one per sub-partition), per iteration: k = 0: 8 x cvt.rn.satfinite.f16x2.f32;
 //          k = 1: 8 x ex2 + 4 x cvt (the softmax mix); k = 2: 8 x fma.rn.f32x2; k = 3: 8 x ex2 + 8 x fma.rn.f32x2 -
 //          which of these share an execution pipe (clock64 cycles of warp 0 for n_mma iterations).
+//   flavor 24 / 25: tanh.approx.f32 / rcp.approx.f32 issue rate, one warp per sub-partition (as flavor 17 for ex2).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int flavor, int n_mma,
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
+template <int OP>  // 0: ex2.approx, 1: tanh.approx, 2: rcp.approx
 __global__ void __launch_bounds__(384, 1) mufu_rate_kernel(int n, unsigned long long* out, float seed) {
   float v[8];
 #pragma unroll
@@ -82,7 +84,11 @@ __global__ void __launch_bounds__(384, 1) mufu_rate_kernel(int n, unsigned long 
   const long long t0 = clock64();
   for (int it = 0; it < n; ++it) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+    for (int i = 0; i < 8; ++i) {
+      if (OP == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+      else if (OP == 1) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
+      else asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+    }
   }
   const long long t1 = clock64();
   float acc = 0.f;
@@ -135,15 +141,20 @@ __global__ void __launch_bounds__(128, 1) pipe_mix_kernel(int mode, int n, unsig
 }  // namespace
 
 extern "C" int mmvid_debug_mma_rate(int flavor, int n_mma, unsigned long long* dev_out, mmvid_stream_t stream) {
-  MMVID_REQUIRE(((flavor >= 0 && flavor <= 8) || (flavor >= 16 && flavor <= 23)) && n_mma > 0 && dev_out != nullptr,
-                "flavor 0..8 or 16..23");
+  MMVID_REQUIRE(((flavor >= 0 && flavor <= 8) || (flavor >= 16 && flavor <= 25)) && n_mma > 0 && dev_out != nullptr,
+                "flavor 0..8 or 16..25");
+  if (flavor == 24 || flavor == 25) {  // tanh.approx / rcp.approx, one warp per sub-partition
+    if (flavor == 24) mufu_rate_kernel<1><<<1, 128, 0, to_stream(stream)>>>(n_mma, dev_out, 0.37f);
+    else mufu_rate_kernel<2><<<1, 128, 0, to_stream(stream)>>>(n_mma, dev_out, 0.37f);
+    return check_launch("mufu_rate");
+  }
   if (flavor >= 20) {
     pipe_mix_kernel<<<1, 128, 0, to_stream(stream)>>>(flavor - 20, n_mma, dev_out, 0.37f);
     return check_launch("pipe_mix");
   }
   if (flavor >= 16) {
     const int warps = flavor == 16 ? 1 : 4 * (flavor - 16);
-    mufu_rate_kernel<<<1, 32 * warps, 0, to_stream(stream)>>>(n_mma, dev_out, 0.37f);
+    mufu_rate_kernel<0><<<1, 32 * warps, 0, to_stream(stream)>>>(n_mma, dev_out, 0.37f);
     return check_launch("mufu_rate");
   }
   static bool attr_set = false;

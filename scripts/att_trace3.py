@@ -17,6 +17,10 @@ for k, w in enumerate((1, 4, 8, 12)):
     torch.cuda.synchronize()
     t = out.cpu().tolist()
     print(f"MUFU.EX2 {w:2d} warps: {t[0] / 16000:.2f} clk per warp instruction (warp 0), {t[1] / 16000:.2f} (last warp)")
+for fl, nm in ((24, "tanh.approx"), (25, "rcp.approx")):
+    L.check(lib.mmvid_debug_mma_rate(fl, 2000, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    print(f"MUFU {nm}: {out.cpu().tolist()[0] / 16000:.2f} clk per warp instruction (one warp per sub-partition)")
 for k, (nm, per) in enumerate((("8 x cvt.f16x2", 8), ("8 x ex2 + 4 x cvt.f16x2", 12), ("8 x fma.f32x2", 8), ("8 x ex2 + 8 x fma.f32x2", 16))):
     L.check(lib.mmvid_debug_mma_rate(20 + k, 2000, out.data_ptr(), None))
     torch.cuda.synchronize()

@@ -10,7 +10,7 @@ lib = L.load()
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp16"
 dt = ops.act_dtype(prec)
 M = 8460
-for (N, K, name, act, res, odt) in [(3072, 768, "c_fc", 1, False, dt), (768, 3072, "c_proj", 0, True, torch.float32),
+for (N, K, name, act, res, odt) in [(3072, 768, "c_fc", 1, False, dt), (3072, 768, "c_fc_noact", 0, False, dt), (768, 3072, "c_proj", 0, True, torch.float32),
                                     (768, 768, "out_proj", 0, True, torch.float32), (1024, 768, "head", 0, False, torch.float32)]:
     a = torch.randn(M, K, device="cuda").to(dt)
     w = (torch.randn(N, K, device="cuda") / 30).to(dt)
