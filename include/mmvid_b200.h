@@ -197,14 +197,27 @@ int mmvid_codebook_gather(const int64_t* ids, const float* codebook, float* out,
  *   precision MMVID_TF32 / MMVID_F16: implicit GEMM on tcgen05 whose pixel tiles are fetched by 4-D TMA boxes (halo taps =
  *   TMA zero fill); MMVID_F16 takes fp16 activations (written by mmvid_groupnorm / mmvid_upsample2x) and fp16 packed
  *   weights, accumulates in fp32 and writes fp32 (bias / residual fp32): the tf32 mantissa at twice the MMA rate.
+ *   gn_partial (optional): the tensor-core conv ALSO writes the GroupNorm partial statistics of its result (after bias and
+ *   residual; model.py:33-42 `Normalize` is what consumes every conv output of the VQGAN): floats
+ *   [N*Ho*Wo/32][gn_groups][2] = per 32-pixel slab and group (sum, sum of squared deviations from the slab mean); mmvid_groupnorm_from_partials turns them
+ *   into the normalised tensor without another statistics pass over the activation.  Only where mmvid_conv2d_gn_fusable()
+ *   returns 1 (tensor-core path, H*W % 128 == 0, Cout % 32 == 0, 4 / 8 / 16 channels per group); refused otherwise.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* in; const void* w; /* fp32; fp16 when precision == MMVID_F16 (tensor-core conv: stride 1, NHWC, Cin % 64 == 0) */
   const float* bias; const float* residual; float* out;
   int N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, upsample;
   int in_nchw, out_nchw, pre_affine, post_clamp, precision;
+  float* gn_partial; int gn_groups;
 } mmvid_conv_params;
 int mmvid_conv2d(const mmvid_conv_params* p, mmvid_stream_t stream);
+int mmvid_conv2d_gn_fusable(const mmvid_conv_params* p);
+
+/* K11 with the statistics taken from a conv's fused partial sums (see mmvid_conv_params::gn_partial): partial holds
+ *   [N*HW/32][groups][2] floats, stats is a caller-owned scratch of N*groups*2 floats; otherwise as mmvid_groupnorm. */
+int mmvid_groupnorm_from_partials(const float* in, void* out, int out_dtype, const float* gamma, const float* beta,
+                                  const float* partial, float* stats, int N, int HW, int C, int groups, float eps, int swish,
+                                  mmvid_stream_t stream);
 
 /* K11 GroupNorm(32 groups, eps) + optional swish on NHWC (model.py:38-42, 33-35):
  *   stats scratch: mmvid_groupnorm_scratch_floats(N, groups) floats.  out may alias in.
@@ -225,6 +238,11 @@ int mmvid_groupnorm_stats(const float* in, float* stats_scratch, int N, int HW, 
 int mmvid_conv_out_fused(const float* in, const float* gamma, const float* beta, const float* w, const float* bias,
                          float* out, float* stats_scratch, int N, int H, int W, int C, int Cout, int groups, float eps,
                          int post_clamp, mmvid_stream_t stream);
+/* ... with norm_out's statistics taken from the producing conv's fused partial sums (mmvid_conv_params::gn_partial);
+ * stats: caller-owned scratch of N*groups*2 floats */
+int mmvid_conv_out_fused_from_partials(const float* in, const float* gamma, const float* beta, const float* w,
+                                       const float* bias, float* out, const float* partial, float* stats, int N, int H,
+                                       int W, int C, int Cout, int groups, float eps, int post_clamp, mmvid_stream_t stream);
 
 /* nearest x2 upsample NHWC (used only when not fused into the conv) */
 int mmvid_upsample2x(const float* in, void* out, int out_dtype /* F32 | F16 */, int N, int H, int W, int C,

@@ -53,7 +53,8 @@ class AdamTensor(C.Structure):
 class ConvParams(C.Structure):
     _fields_ = [("inp", _p), ("w", _p), ("bias", _p), ("residual", _p), ("out", _p)] + \
                [(n, _i) for n in ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad_t", "pad_l", "Ho", "Wo",
-                                  "upsample", "in_nchw", "out_nchw", "pre_affine", "post_clamp", "precision")]
+                                  "upsample", "in_nchw", "out_nchw", "pre_affine", "post_clamp", "precision")] + \
+               [("gn_partial", _p), ("gn_groups", _i)]
 
 
 # name -> (restype, argtypes); kept in sync with include/mmvid_b200.h (tests/test_abi.py checks every symbol)
@@ -85,10 +86,13 @@ SIGNATURES = {
     "mmvid_vq_argmin": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "mmvid_codebook_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "mmvid_conv2d": (_i, [C.POINTER(ConvParams), _p]),
+    "mmvid_conv2d_gn_fusable": (_i, [C.POINTER(ConvParams)]),
+    "mmvid_groupnorm_from_partials": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "mmvid_groupnorm": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "mmvid_groupnorm_scratch_floats": (_ll, [_i, _i]),
     "mmvid_groupnorm_stats": (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     "mmvid_conv_out_fused": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "mmvid_conv_out_fused_from_partials": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "mmvid_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "mmvid_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _p]),
     "mmvid_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -537,15 +537,8 @@ extern "C" int mmvid_groupnorm_stats(const float* in, float* stats, int N, int H
   return groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, to_stream(stream));
 }
 
-extern "C" int mmvid_groupnorm(const float* in, void* out, int out_dtype, const float* gamma, const float* beta,
-                               float* stats, int N, int HW, int C, int groups, float eps, int swish,
-                               mmvid_stream_t stream) {
-  MMVID_REQUIRE(C % groups == 0 && C % 4 == 0 && C <= 1024, "C divisible by groups and 4, <= 1024");
-  MMVID_REQUIRE(out_dtype == MMVID_DT_F32 || out_dtype == MMVID_DT_F16, "fp32 or fp16 output");
-  if (N == 0) return MMVID_OK;
-  cudaStream_t st = to_stream(stream);
-  int rc = groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, st);
-  if (rc) return rc;
+static int groupnorm_apply_launch(const float* in, void* out, int out_dtype, const float* gamma, const float* beta,
+                                  const float* stats, int N, int HW, int C, int groups, int swish, cudaStream_t st) {
   const int C4 = C / 4;
   if (C4 <= 256 && 256 % C4 == 0 && N <= 65535) {
     const int ppb = 256 / C4;
@@ -569,6 +562,70 @@ extern "C" int mmvid_groupnorm(const float* in, void* out, int out_dtype, const 
   groupnorm_apply_kernel<<<blocks, 256, 0, st>>>((const float4*)in, (float4*)out, gamma, beta, stats, HW, C, groups,
                                                   swish, total4);
   return check_launch("groupnorm_apply");
+}
+
+extern "C" int mmvid_groupnorm(const float* in, void* out, int out_dtype, const float* gamma, const float* beta,
+                               float* stats, int N, int HW, int C, int groups, float eps, int swish,
+                               mmvid_stream_t stream) {
+  MMVID_REQUIRE(C % groups == 0 && C % 4 == 0 && C <= 1024, "C divisible by groups and 4, <= 1024");
+  MMVID_REQUIRE(out_dtype == MMVID_DT_F32 || out_dtype == MMVID_DT_F16, "fp32 or fp16 output");
+  if (N == 0) return MMVID_OK;
+  cudaStream_t st = to_stream(stream);
+  int rc = groupnorm_stats_launch(in, stats, N, HW, C, groups, eps, st);
+  if (rc) return rc;
+  return groupnorm_apply_launch(in, out, out_dtype, gamma, beta, stats, N, HW, C, groups, swish, st);
+}
+
+// Statistics from the partial statistics a tensor-core conv wrote next to its result (EpiArgs::gn_partial, tc_gemm.cu):
+// partial[(slab * G + g) * 2 + {0, 1}] = (sum, sum of squared deviations from the slab's own mean) of 32 pixels x (C / G)
+// channels, HW / 32 slabs per image.  One block per image, thread = (group, slab lane); the slabs are combined with the
+// parallel-variance formula  M2 = sum_i [M2_i + n_i (mean_i - mean)^2]  in double and in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024) groupnorm_finalize_partials_kernel(const float* __restrict__ partial,
+                                                                           float* __restrict__ stats, int spi, int G,
+                                                                           int n_slab, float eps) {
+  __shared__ double red[1024];
+  __shared__ double mean_s[512];
+  const int n = blockIdx.x, g = threadIdx.x % G, sl = threadIdx.x / G, nsl = blockDim.x / G;
+  const float2* base = reinterpret_cast<const float2*>(partial) + (long long)n * spi * G + g;
+  double acc = 0.0;
+  for (int s = sl; s < spi; s += nsl) acc += (double)base[(long long)s * G].x;
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (sl == 0) {
+    for (int k = 1; k < nsl; ++k) acc += red[k * G + g];
+    mean_s[g] = acc / ((double)spi * n_slab);
+  }
+  __syncthreads();
+  const double mean = mean_s[g], inv_n = 1.0 / n_slab;
+  acc = 0.0;
+  for (int s = sl; s < spi; s += nsl) {
+    const float2 v = base[(long long)s * G];
+    const double d = (double)v.x * inv_n - mean;
+    acc += (double)v.y + n_slab * d * d;
+  }
+  __syncthreads();
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (sl == 0) {
+    for (int k = 1; k < nsl; ++k) acc += red[k * G + g];
+    const double var = acc / ((double)spi * n_slab);
+    stats[((long long)n * G + g) * 2 + 0] = (float)mean;
+    stats[((long long)n * G + g) * 2 + 1] = rsqrtf((float)var + eps);
+  }
+}
+
+extern "C" int mmvid_groupnorm_from_partials(const float* in, void* out, int out_dtype, const float* gamma, const float* beta,
+                                             const float* partial, float* stats, int N, int HW, int C, int groups, float eps,
+                                             int swish, mmvid_stream_t stream) {
+  MMVID_REQUIRE(C % groups == 0 && C % 4 == 0 && C <= 1024, "C divisible by groups and 4, <= 1024");
+  MMVID_REQUIRE(out_dtype == MMVID_DT_F32 || out_dtype == MMVID_DT_F16, "fp32 or fp16 output");
+  MMVID_REQUIRE(HW % 32 == 0 && groups >= 1 && groups <= 512 && 1024 % groups == 0, "HW % 32 == 0, groups divides 1024");
+  if (N == 0) return MMVID_OK;
+  cudaStream_t st = to_stream(stream);
+  groupnorm_finalize_partials_kernel<<<N, 1024, 0, st>>>(partial, stats, HW / 32, groups, 32 * (C / groups), eps);
+  int rc = check_launch("groupnorm_finalize_partials");
+  if (rc) return rc;
+  return groupnorm_apply_launch(in, out, out_dtype, gamma, beta, stats, N, HW, C, groups, swish, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -657,15 +714,9 @@ __global__ void __launch_bounds__(256) conv_out_fused_kernel(const float* __rest
   }
 }
 
-extern "C" int mmvid_conv_out_fused(const float* in, const float* gamma, const float* beta, const float* w,
-                                    const float* bias, float* out, float* stats_scratch, int N, int H, int W, int C,
-                                    int Cout, int groups, float eps, int post_clamp, mmvid_stream_t stream) {
-  MMVID_REQUIRE(Cout >= 1 && Cout <= 4, "1..4 output channels");
-  MMVID_REQUIRE(C % CO_CH == 0 && C % groups == 0, "C multiple of 32 and of groups");
-  if (N == 0) return MMVID_OK;
-  cudaStream_t st = to_stream(stream);
-  int rc = groupnorm_stats_launch(in, stats_scratch, N, H * W, C, groups, eps, st);
-  if (rc) return rc;
+static int conv_out_fused_launch(const float* in, const float* gamma, const float* beta, const float* w, const float* bias,
+                                 float* out, const float* stats, int N, int H, int W, int C, int Cout, int groups,
+                                 int post_clamp, cudaStream_t st) {
   const size_t smem = ((size_t)(CO_TH + 2) * (CO_TW + 2) * CO_LD + 4 * 9 * CO_CH) * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -676,12 +727,38 @@ extern "C" int mmvid_conv_out_fused(const float* in, const float* gamma, const f
   dim3 grid(ceil_div(W, CO_TW), ceil_div(H, CO_TH), N);
   // post_clamp bit 0: clamp + rescale to [0, 1]; bit 1: swish through MUFU ex2 / rcp instead of expf + IEEE division
   if (post_clamp & 2)
-    conv_out_fused_kernel<true><<<grid, 256, smem, st>>>(in, stats_scratch, gamma, beta, w, bias, out, H, W, C, groups, Cout,
-                                                         post_clamp & 1);
+    conv_out_fused_kernel<true><<<grid, 256, smem, st>>>(in, stats, gamma, beta, w, bias, out, H, W, C, groups, Cout, post_clamp & 1);
   else
-    conv_out_fused_kernel<false><<<grid, 256, smem, st>>>(in, stats_scratch, gamma, beta, w, bias, out, H, W, C, groups, Cout,
-                                                          post_clamp & 1);
+    conv_out_fused_kernel<false><<<grid, 256, smem, st>>>(in, stats, gamma, beta, w, bias, out, H, W, C, groups, Cout, post_clamp & 1);
   return check_launch("conv_out_fused");
+}
+
+extern "C" int mmvid_conv_out_fused(const float* in, const float* gamma, const float* beta, const float* w,
+                                    const float* bias, float* out, float* stats_scratch, int N, int H, int W, int C,
+                                    int Cout, int groups, float eps, int post_clamp, mmvid_stream_t stream) {
+  MMVID_REQUIRE(Cout >= 1 && Cout <= 4, "1..4 output channels");
+  MMVID_REQUIRE(C % CO_CH == 0 && C % groups == 0, "C multiple of 32 and of groups");
+  if (N == 0) return MMVID_OK;
+  cudaStream_t st = to_stream(stream);
+  int rc = groupnorm_stats_launch(in, stats_scratch, N, H * W, C, groups, eps, st);
+  if (rc) return rc;
+  return conv_out_fused_launch(in, gamma, beta, w, bias, out, stats_scratch, N, H, W, C, Cout, groups, post_clamp, st);
+}
+
+// the same with the statistics taken from the producing conv's fused partial sums (mmvid_conv_params::gn_partial)
+extern "C" int mmvid_conv_out_fused_from_partials(const float* in, const float* gamma, const float* beta, const float* w,
+                                                  const float* bias, float* out, const float* partial, float* stats, int N,
+                                                  int H, int W, int C, int Cout, int groups, float eps, int post_clamp,
+                                                  mmvid_stream_t stream) {
+  MMVID_REQUIRE(Cout >= 1 && Cout <= 4, "1..4 output channels");
+  MMVID_REQUIRE(C % CO_CH == 0 && C % groups == 0, "C multiple of 32 and of groups");
+  MMVID_REQUIRE((H * W) % 32 == 0 && groups <= 512 && 1024 % groups == 0, "H*W % 32 == 0, groups divides 1024");
+  if (N == 0) return MMVID_OK;
+  cudaStream_t st = to_stream(stream);
+  groupnorm_finalize_partials_kernel<<<N, 1024, 0, st>>>(partial, stats, H * W / 32, groups, 32 * (C / groups), eps);
+  int rc = check_launch("groupnorm_finalize_partials");
+  if (rc) return rc;
+  return conv_out_fused_launch(in, gamma, beta, w, bias, out, stats, N, H, W, C, Cout, groups, post_clamp, st);
 }
 
 // ------------------------------------------------------------------------------------------------

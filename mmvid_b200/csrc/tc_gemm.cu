@@ -84,11 +84,55 @@ struct EpiArgs {
   // QKV mode (qkv_q != nullptr): the [M, 3*H*64] result is scattered straight into the attention layout
   //   Q,K -> [B,H,S_pad,64]   V -> V^T [B,H,64,S_pad]   (fp32 or 16-bit via c_h16); bias applied, no act/residual
   void* qkv_q; void* qkv_k; void* qkv_vt; int qS, qSpad, qH;
+  // GroupNorm statistics of the RESULT, fused (conv path, fp32 TMA-store epilogue): every epilogue warp writes the sum and
+  // the sum of squared deviations from its own mean of its 32 pixels x 32 channels per group to
+  // gn_partial[((m_tile * 4 + q) * gn_G + group) * 2 + {0, 1}]
+  // (each entry is written by exactly one warp: deterministic), mmvid_groupnorm_from_partials reduces them per image.
+  float* gn_partial; int gn_cpg, gn_G;
   int tma_store;  // 1: result tiles leave through TMA bulk stores (tmC; tmC1 for lone 16-bit chunks), see the epilogue
   unsigned long long* trace;  // debug timeline of CTA 0 (mmvid_debug_gemm_trace), normally null
   int spin;    // 1: the TMA / MMA threads poll their ring barriers (mbar_wait_spin) instead of suspending in try_wait
   int raster;  // 0: m fastest; 1: n fastest; 2: 8-wide n groups (each wave covers ~8 weight tiles x ~18 row tiles)
 };
+
+// per-group partial statistics of one 32-pixel x 32-channel result chunk (lane = pixel, o = its 32 channels), see
+// EpiArgs::gn_partial: (sum, sum of squared deviations from the SLAB's own mean) - the finaliser combines the slabs with the
+// parallel-variance formula, so a group whose mean is large against its spread loses nothing to cancellation.
+template <int CPG>
+__device__ __forceinline__ void gn_chunk_partials(const float (&o)[32], float* dst, int lane) {
+  constexpr int NG = 32 / CPG;
+  float s[NG], m2[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) a += o[g * CPG + c];
+    s[g] = a;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], off);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float mu = s[g] * (1.f / (32 * CPG));
+    float b = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+      const float d = o[g * CPG + c] - mu;
+      b = fmaf(d, d, b);
+    }
+    m2[g] = b;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) m2[g] += __shfl_xor_sync(0xffffffffu, m2[g], off);
+  if (lane == 0) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) *reinterpret_cast<float2*>(dst + 2 * g) = make_float2(s[g], m2[g]);
+  }
+}
 
 // tile index -> (m tile, n tile)
 __device__ __forceinline__ void tile_coords(const EpiArgs& e, int tile, int& mt, int& nt) {
@@ -361,6 +405,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               for (int i = 0; i < 8; ++i) {
                 o[4 * i + 0] += res[cc][i].x; o[4 * i + 1] += res[cc][i].y;
                 o[4 * i + 2] += res[cc][i].z; o[4 * i + 3] += res[cc][i].w;
+              }
+            }
+            if constexpr (CONV && !H16) {
+              if (e.gn_partial != nullptr) {  // warp-uniform; rows are always valid here (M % 128 == 0 is a precondition)
+                float* dst = e.gn_partial + (((long long)mt * 4 + q) * e.gn_G + ncol / e.gn_cpg) * 2;
+                if (e.gn_cpg == 4) gn_chunk_partials<4>(o, dst, lane);
+                else if (e.gn_cpg == 8) gn_chunk_partials<8>(o, dst, lane);
+                else gn_chunk_partials<16>(o, dst, lane);
               }
             }
             if constexpr (H16) {
@@ -807,6 +859,23 @@ extern "C" int mmvid_linear_tc(const void* A, int a_dtype, long long lda, const 
 // Requirements: stride 1, Cin % 32 == 0, Cout % 4 == 0, H and W powers of two, NHWC in/out.
 // Everything else (first 3-channel conv, stride-2 downsample, 3-channel output conv) stays on the fp32 path.
 // ------------------------------------------------------------------------------------------------
+extern "C" int mmvid_conv2d_gn_fusable(const mmvid_conv_params* p) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!(p->precision == MMVID_TF32 || p->precision == MMVID_F16)) return 0;
+  if (p->stride != 1 || p->in_nchw || p->out_nchw || p->pre_affine || p->post_clamp || p->upsample || p->KH != 3 || p->KW != 3) return 0;
+  if (!pow2(p->H) || !pow2(p->W) || p->Ho != p->H || p->Wo != p->W || ((long long)p->H * p->W) % 128 != 0) return 0;
+  if (p->gn_groups <= 0 || p->Cout % p->gn_groups != 0 || p->Cout % 32 != 0) return 0;
+  const int cpg = p->Cout / p->gn_groups;
+  if (cpg != 4 && cpg != 8 && cpg != 16) return 0;
+  if (p->precision == MMVID_TF32 && env_int("MMVID_CONV_SWAP", 0)) return 0;
+  // the TMA-store epilogue's own preconditions (launch<>): 16-byte aligned result / residual / bias
+  if (!env_int("MMVID_GEMM_TMA_STORE", GEMM_TMA_STORE_DEFAULT) || !al16(p->out) || (p->residual && !al16(p->residual)) ||
+      (p->bias && !al16(p->bias)))
+    return 0;
+  return 1;
+}
+
 extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
   MMVID_REQUIRE(p->precision == MMVID_TF32 || p->precision == MMVID_F16, "tensor-core conv runs kind::tf32 or kind::f16 (fp16)");
@@ -873,6 +942,14 @@ extern "C" int mmvid_conv2d_tc(const mmvid_conv_params* p, cudaStream_t st) {
   e.M = M; e.N = p->Cout; e.K = K; e.act = MMVID_ACT_NONE;
   e.cCin = p->Cin; e.cKW = p->KW; e.cPadT = p->pad_t; e.cPadL = p->pad_l; e.cBW = BW; e.cBH = BH; e.cBNI = BNI;
   e.cW = p->W; e.cH = p->H;
+  if (p->gn_partial != nullptr) {
+    // fused GroupNorm statistics of the result: one image per pixel tile, whole groups per 32-channel chunk, and the
+    // fp32 TMA-store epilogue (the only one that carries the hook) - refused loudly otherwise (mmvid_conv2d_gn_fusable)
+    const int cpg = p->gn_groups > 0 ? p->Cout / p->gn_groups : 0;
+    MMVID_REQUIRE(mmvid_conv2d_gn_fusable(p) == 1, "conv: fused GroupNorm statistics need the tensor-core path, H*W % 128 == 0, "
+                                                   "Cout % 32 == 0 and 4, 8 or 16 channels per group");
+    e.gn_partial = p->gn_partial; e.gn_cpg = cpg; e.gn_G = p->gn_groups;
+  }
   return f16 ? launch_bn<false, true>(BN, tmA, tmB, e, st) : launch_bn<true, true>(BN, tmA, tmB, e, st);
 }
 

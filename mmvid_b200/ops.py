@@ -116,15 +116,25 @@ def layernorm(x, weight, bias, eps=1e-5, out_dtype=torch.float32):
     return out.view(*x.shape[:-1], D)
 
 
-def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None, fast=False, out_dtype=torch.float32):
+def groupnorm(x_nhwc, weight, bias, groups=32, eps=1e-6, swish=False, out=None, fast=False, out_dtype=torch.float32,
+              partial=None):
     """x: float32 [N, H, W, C] contiguous.  fast: swish through MUFU ex2 / rcp (tensor-core precision modes).
-    out_dtype=torch.float16: the result feeds a kind::f16 conv (not in place)."""
+    out_dtype=torch.float16: the result feeds a kind::f16 conv (not in place).
+    partial: per-slab (sum, squared deviations) the conv that produced x wrote next to it (conv2d(..., gn_groups=)): the
+    statistics pass over x is skipped."""
     lib = L.load()
     _req(x_nhwc, torch.float32, "x")
     assert x_nhwc.is_contiguous()
     N, H, W, Cc = x_nhwc.shape
     if out is None or out.dtype != out_dtype:
         out = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=out_dtype)
+    if partial is not None:
+        assert partial.dtype == torch.float32 and partial.numel() == N * H * W // 32 * groups * 2
+        stats = torch.empty(N * groups * 2, device=x_nhwc.device, dtype=torch.float32)
+        L.check(lib.mmvid_groupnorm_from_partials(_ptr(x_nhwc), _ptr(out), _dt(out), _ptr(weight), _ptr(bias), _ptr(partial),
+                                                  _ptr(stats), N, H * W, Cc, groups, eps, (2 if fast else 1) if swish else 0,
+                                                  _stream()), "groupnorm_from_partials")
+        return out
     stats = torch.empty(int(lib.mmvid_groupnorm_scratch_floats(N, groups)), device=x_nhwc.device, dtype=torch.float32)
     L.check(lib.mmvid_groupnorm(_ptr(x_nhwc), _ptr(out), _dt(out), _ptr(weight), _ptr(bias), _ptr(stats), N, H * W, Cc,
                                 groups, eps, (2 if fast else 1) if swish else 0, _stream()), "groupnorm")
@@ -343,9 +353,11 @@ def codebook_gather(ids, codebook):
 
 
 def conv2d(x, w_packed, bias, *, stride=1, pad=(1, 1), out_hw=None, upsample=False, residual=None, in_nchw=False,
-           out_nchw=False, pre_affine=False, post_clamp=False, precision=FP32):
+           out_nchw=False, pre_affine=False, post_clamp=False, precision=FP32, gn_groups=0):
     """x: float32 NHWC [N,H,W,Cin] (or NCHW if in_nchw); w_packed [Cout,KH,KW,Cin]; returns float32 NHWC (or NCHW).
-    precision 'fp16': x and w_packed are float16 (kind::f16 implicit GEMM, fp32 accumulate / bias / residual / output)."""
+    precision 'fp16': x and w_packed are float16 (kind::f16 implicit GEMM, fp32 accumulate / bias / residual / output).
+    gn_groups > 0: returns (out, partial) where partial holds the GroupNorm partial statistics of `out` for
+    groupnorm(..., partial=) - or None where the conv cannot produce them (mmvid_conv2d_gn_fusable)."""
     lib = L.load()
     if precision_id(precision) == F16:
         _req(x, torch.float16)
@@ -375,8 +387,14 @@ def conv2d(x, w_packed, bias, *, stride=1, pad=(1, 1), out_hw=None, upsample=Fal
     p.stride, p.pad_t, p.pad_l, p.Ho, p.Wo = stride, pad[0], pad[1], Ho, Wo
     p.upsample, p.in_nchw, p.out_nchw = int(upsample), int(in_nchw), int(out_nchw)
     p.pre_affine, p.post_clamp, p.precision = int(pre_affine), int(post_clamp), precision_id(precision)
+    partial = None
+    if gn_groups:
+        p.gn_groups = int(gn_groups)
+        if lib.mmvid_conv2d_gn_fusable(C.byref(p)) == 1:
+            partial = torch.empty(N * Ho * Wo // 32 * gn_groups * 2, device=x.device, dtype=torch.float32)
+            p.gn_partial = partial.data_ptr()
     L.check(lib.mmvid_conv2d(C.byref(p), _stream()), "conv2d")
-    return out
+    return (out, partial) if gn_groups else out
 
 
 def upsample2x(x, out_dtype=torch.float32):
@@ -389,8 +407,9 @@ def upsample2x(x, out_dtype=torch.float32):
     return out
 
 
-def conv_out_fused(x_nhwc, gamma, beta, w_packed, bias, groups=32, eps=1e-6, post_clamp=True, fast=False):
-    """GroupNorm + swish + 3x3 conv (Cout <= 4) + clamp/rescale; NHWC float32 in, NCHW out."""
+def conv_out_fused(x_nhwc, gamma, beta, w_packed, bias, groups=32, eps=1e-6, post_clamp=True, fast=False, partial=None):
+    """GroupNorm + swish + 3x3 conv (Cout <= 4) + clamp/rescale; NHWC float32 in, NCHW out.
+    partial: GroupNorm partial statistics of x written by the conv that produced it (conv2d(..., gn_groups=))."""
     lib = L.load()
     _req(x_nhwc, torch.float32)
     assert x_nhwc.is_contiguous() and w_packed.is_contiguous()
@@ -398,6 +417,13 @@ def conv_out_fused(x_nhwc, gamma, beta, w_packed, bias, groups=32, eps=1e-6, pos
     Cout = w_packed.shape[0]
     assert tuple(w_packed.shape[1:]) == (3, 3, Cc)
     out = torch.empty(N, Cout, H, W, device=x_nhwc.device, dtype=torch.float32)
+    if partial is not None:
+        assert partial.dtype == torch.float32 and partial.numel() == N * H * W // 32 * groups * 2
+        stats = torch.empty(N * groups * 2, device=x_nhwc.device, dtype=torch.float32)
+        L.check(lib.mmvid_conv_out_fused_from_partials(_ptr(x_nhwc), _ptr(gamma), _ptr(beta), _ptr(w_packed), _ptr(bias), _ptr(out),
+                                                       _ptr(partial), _ptr(stats), N, H, W, Cc, Cout, groups, eps,
+                                                       int(post_clamp) | (2 if fast else 0), _stream()), "conv_out_fused_from_partials")
+        return out
     stats = torch.empty(int(lib.mmvid_groupnorm_scratch_floats(N, groups)), device=x_nhwc.device, dtype=torch.float32)
     L.check(lib.mmvid_conv_out_fused(_ptr(x_nhwc), _ptr(gamma), _ptr(beta), _ptr(w_packed), _ptr(bias), _ptr(out),
                                      _ptr(stats), N, H, W, Cc, Cout, groups, eps, int(post_clamp) | (2 if fast else 0), _stream()),

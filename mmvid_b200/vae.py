@@ -12,6 +12,7 @@ Same public API (`get_codebook_indices`, `decode`, `decode_train`; attrs `num_la
   1x1 convs are GEMMs over pixel rows; AttnBlock = batched GEMM + row softmax; VQ = fused distance+argmin.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -198,10 +199,21 @@ class VQGanVAE1024(nn.Module):
         tiles (nearest-x2 upsampling is materialised first); the 3-channel input/output convs and the stride-2
         downsample stay on the fp32 implicit-GEMM path.  'fp16' (decoder): a float16 `x` (written by the GroupNorm /
         upsample kernel that precedes the conv) selects the kind::f16 implicit GEMM with fp16 packed weights."""
+        # Decoder, tensor-core modes: every conv result is normalised next (Normalize, model.py:38-42), so the conv writes the
+        # GroupNorm partial statistics of its result from the epilogue and the statistics pass over the activation (1 GB at
+        # 256 px, batch 4 x 8 frames) never runs.  The pair (result, partials) waits in self._gn_slot for _gn().
+        fuse = getattr(self, "_decoding", False) and os.environ.get("MMVID_GN_FUSE", "1") != "0"
+
+        def run(x_, w_, prec):
+            if not fuse or prec == FP32:
+                return ops.conv2d(x_, w_, conv.bias, precision=prec, **kw)
+            out, part = ops.conv2d(x_, w_, conv.bias, precision=prec, gn_groups=32, **kw)
+            self._gn_slot = (out, part) if part is not None else None
+            return out
         if x.dtype == torch.float16:
             w = self._pack.conv(conv.weight, torch.float16)
             assert kw.get("stride", 1) == 1 and not kw.get("upsample") and w.shape[3] % 64 == 0
-            return ops.conv2d(x, w, conv.bias, precision=F16, **kw)
+            return run(x, w, F16)
         w = self._pack.conv(conv.weight)
         tc_ok = (self._prec() != FP32 and kw.get("stride", 1) == 1 and not kw.get("in_nchw") and not kw.get("out_nchw")
                  and w.shape[3] % 32 == 0 and w.shape[0] % 4 == 0)
@@ -209,9 +221,16 @@ class VQGanVAE1024(nn.Module):
             if kw.pop("upsample", False):
                 x = ops.upsample2x(x, out_dtype=self._act16())
                 if x.dtype == torch.float16:
-                    return ops.conv2d(x, self._pack.conv(conv.weight, torch.float16), conv.bias, precision=F16, **kw)
-            return ops.conv2d(x, w, conv.bias, precision=TF32, **kw)
+                    return run(x, self._pack.conv(conv.weight, torch.float16), F16)
+            return run(x, w, TF32)
         return ops.conv2d(x, w, conv.bias, precision=FP32, **kw)
+
+    def _gn(self, x, norm, **kw):
+        """GroupNorm of x; uses the partial statistics its producing conv left in self._gn_slot (see _conv3)."""
+        slot = getattr(self, "_gn_slot", None)
+        self._gn_slot = None
+        part = slot[1] if slot is not None and slot[0] is x else None
+        return ops.groupnorm(x, norm.weight, norm.bias, partial=part, **kw)
 
     def _act16(self):
         """dtype the GroupNorm / upsample kernels hand to the 3x3 convs: float16 in the decoder of an 'fp16' VQGAN (same
@@ -233,16 +252,16 @@ class VQGanVAE1024(nn.Module):
     def _resblock(self, x, blk):
         fast = self._prec() != FP32  # tensor-core modes: MUFU sigmoid; fp32 parity mode keeps expf + IEEE division
         a16 = self._act16()
-        t = ops.groupnorm(x, blk.norm1.weight, blk.norm1.bias, swish=True, fast=fast, out_dtype=a16)
+        t = self._gn(x, blk.norm1, swish=True, fast=fast, out_dtype=a16)
         t = self._conv3(t, blk.conv1)
-        t = ops.groupnorm(t, blk.norm2.weight, blk.norm2.bias, swish=True, out=t, fast=fast, out_dtype=a16)
+        t = self._gn(t, blk.norm2, swish=True, out=t, fast=fast, out_dtype=a16)
         sc = x if blk.in_channels == blk.out_channels else self._conv1(x, blk.nin_shortcut)
         return self._conv3(t, blk.conv2, residual=sc)
 
     def _attnblock(self, x, blk):
         N, H, W, C = x.shape
         HW = H * W
-        t = ops.groupnorm(x, blk.norm.weight, blk.norm.bias, swish=False)
+        t = self._gn(x, blk.norm, swish=False)
         wqkv = self._pack.cat(("qkv", id(blk)), [blk.q.weight, blk.k.weight, blk.v.weight])
         bqkv = self._pack.cat(("bqkv", id(blk)), [blk.q.bias, blk.k.bias, blk.v.bias])
         qkv = ops.linear(t.view(-1, C), wqkv, bqkv, precision=self._lin_prec())  # [N*HW, 3C]
@@ -292,10 +311,12 @@ class VQGanVAE1024(nn.Module):
     def _decode_latent(self, z):
         """z: float32 NHWC [N, h, w, 256] codebook vectors -> float [N,3,H,W] in [0,1]."""
         self._decoding = True
+        self._gn_slot = None
         try:
             return self._decode_latent_impl(z)
         finally:
             self._decoding = False
+            self._gn_slot = None
 
     def _decode_latent_impl(self, z):
         dec = self.model.decoder
@@ -313,8 +334,10 @@ class VQGanVAE1024(nn.Module):
             if lvl != 0:
                 h = self._conv3(h, up.upsample.conv, upsample=True)  # nearest x2 folded into the gather (model.py:56-62)
         # norm_out -> swish -> conv_out -> clamp/rescale in one pass over the 128-channel activation
+        slot, self._gn_slot = getattr(self, "_gn_slot", None), None
         return ops.conv_out_fused(h, dec.norm_out.weight, dec.norm_out.bias, self._pack.conv(dec.conv_out.weight),
-                                  dec.conv_out.bias, post_clamp=True, fast=self._prec() != FP32)
+                                  dec.conv_out.bias, post_clamp=True, fast=self._prec() != FP32,
+                                  partial=slot[1] if slot is not None and slot[0] is h else None)
 
     @torch.no_grad()
     def decode(self, img_seq):

@@ -7,7 +7,7 @@ import torch
 
 from cases import ARTV_CASES, BERT_CASES, TRANSFORMER_CASES, VAE_CASES
 from helpers import (artv_spec, bert_spec, build_artv, build_bert, build_vae, load_fixture, relerr, to_device)
-from mmvid_b200 import synth
+from mmvid_b200 import _lib, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -97,6 +97,33 @@ def test_vae_decode_fp16_tensor_core_pixels_and_encoder_untouched(name):
           f"{mm32}/{idx32.numel()} (tf32 module) - bit-exact indices are the fp32 module's contract")
     assert e < 1e-3
     assert torch.equal(idx16, idx32)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "fp16"])
+def test_vae_decode_with_conv_fused_groupnorm_statistics_equals_the_two_pass_path(monkeypatch, prec):
+    """Decoder convs write the GroupNorm partial statistics of their results (MMVID_GN_FUSE=1, default): same pixels as with
+    the separate statistics pass (MMVID_GN_FUSE=0) up to the summation order of the statistics."""
+    cfg = VAE_CASES["vae_128"]
+    fx = load_fixture("vae_128")
+    vae, _ = build_vae(cfg["image_size"], cfg["seed"], precision=prec)
+    ids = fx["indices"].cuda()
+    monkeypatch.setenv("MMVID_GN_FUSE", "0")
+    two_pass = vae.decode(ids)
+    monkeypatch.setenv("MMVID_GN_FUSE", "1")
+    n0 = _lib.launch_count()
+    fused = vae.decode(ids)
+    n_fused = _lib.launch_count() - n0
+    monkeypatch.setenv("MMVID_GN_FUSE", "0")
+    n0 = _lib.launch_count()
+    vae.decode(ids)
+    n_two = _lib.launch_count() - n0
+    e = relerr(fused, two_pass)
+    print(f"vae_128 {prec}: fused-statistics decode vs two-pass decode relerr {e:.2e}; launches {n_fused} vs {n_two}; "
+          f"vs reference {relerr(fused, fx['decoded']):.2e}")
+    # (statistics that agree to ~1e-6 still move some activations across a 10-bit rounding boundary of the next conv's
+    # operands: the two decodes are two realisations of the same rounding noise, each equally far from the reference)
+    assert e < 1e-3 and relerr(fused, fx["decoded"]) < 1e-3
+    assert n_fused < n_two  # statistics kernels actually left the launch list
 
 
 # ------------------------------------------------------------------------------------------------ BERT

@@ -502,6 +502,38 @@ def test_attention_speculative_exponentials_match_the_exact_max_path(monkeypatch
         assert e < tol * (3 if name == "climbing_max" else 1), f"{prec} spec={spec} {name}: {e}"
 
 
+@pytest.mark.parametrize("prec", ["tf32", "fp16"])
+@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 128, 128, 32), (3, 256, 128, 16), (1, 128, 256, 64), (2, 512, 512, 16)])
+def test_conv_epilogue_groupnorm_partials_match_a_statistics_pass(prec, N, Cin, Cout, H):
+    """The tensor-core conv writes the GroupNorm partial statistics of its result (after bias and residual) from the
+    epilogue; groupnorm(partial=) must give what the ordinary two-kernel statistics pass over the same result gives, and the
+    conv result itself must not change."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 100 + Cout + H)
+    x = (torch.randn(N, H, H, Cin, generator=g) * 1.5 + 0.3).cuda()
+    w = (torch.randn(Cout, 3, 3, Cin, generator=g) / math.sqrt(Cin * 9)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    res = (torch.randn(N, H, H, Cout, generator=g) + 2.0).cuda()      # shifts the mean: sums are not centred in the epilogue
+    gw, gb = torch.randn(Cout, generator=g).cuda(), torch.randn(Cout, generator=g).cuda()
+    if prec == "fp16":
+        x, w = x.half(), w.half()
+    plain = ops.conv2d(x, w, b, residual=res, precision=prec)
+    out, part = ops.conv2d(x, w, b, residual=res, precision=prec, gn_groups=32)
+    assert part is not None, "these shapes are fusable"
+    assert torch.equal(out, plain)
+    for swish, dt in ((True, torch.float16), (False, torch.float32)):
+        ref = ops.groupnorm(out, gw, gb, swish=swish, fast=True, out_dtype=dt).float()
+        got = ops.groupnorm(out, gw, gb, swish=swish, fast=True, out_dtype=dt, partial=part).float()
+        e = relerr(got, ref)
+        assert e < (2e-3 if dt == torch.float16 else 2e-6), e   # fp16: one-ulp flips of the 16-bit rounding
+    ref64 = F.group_norm(out.permute(0, 3, 1, 2).double(), 32, gw.double(), gb.double(), 1e-6).permute(0, 2, 3, 1).float()
+    assert relerr(ops.groupnorm(out, gw, gb, partial=part), ref64) < 5e-6
+    # not fusable: 8 x 8 images (two images per pixel tile) -> no partials, plain result
+    xs = x[:, :8, :8].contiguous()
+    o2, p2 = ops.conv2d(xs, w, b, precision=prec, gn_groups=32)
+    assert p2 is None and torch.equal(o2, ops.conv2d(xs, w, b, precision=prec))
+
+
 def test_groupnorm_streaming_kernel_exact_and_fast_swish():
     """groupnorm_apply2 (one channel quad per thread) for every VQGAN width, exact (expf / IEEE division) and MUFU swish."""
     ops = _ops()
