@@ -383,10 +383,22 @@ class DALLE(nn.Module):
                 logits_buf.copy_(saved_logits)
                 t_dev.zero_()
             cur.wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
+            # Manual capture instead of `with torch.cuda.graph(...)`: the context manager empties the caching allocator on
+            # entry (cudaFree of every cached block, then cudaMalloc again for the VQGAN decode that follows) - 0.1-0.7 s of
+            # host time per generate_images call on a busy box, inside the benchmark's timed region.
+            def capture(n_tokens, pool=None):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    g_.capture_begin(*(() if pool is None else (pool,)))
+                    try:
+                        for _ in range(n_tokens):
+                            token_step()
+                    finally:
+                        g_.capture_end()
+                return g_
+            side.wait_stream(cur)
             n0 = L.launch_count()
-            with torch.cuda.graph(graph):
-                token_step()
+            graph = capture(1)
             per_replay = L.launch_count() - n0
             # ... and GROUP token steps in a second graph: 2047 replays of an 8-node graph are ~2047 host round trips
             # (20-400 us each, depending on how busy the host is - one bench leg measured 1.67 s instead of 0.9 s on a noisy
@@ -395,10 +407,8 @@ class DALLE(nn.Module):
             todo = n_steps - 1
             graph_n = None
             if todo >= 2 * GROUP:
-                graph_n = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph_n):
-                    for _ in range(GROUP):
-                        token_step()
+                graph_n = capture(GROUP, graph.pool())
+            cur.wait_stream(side)
             captured = L.launch_count()
             logits_buf.copy_(saved_logits)
             t_dev.zero_()
