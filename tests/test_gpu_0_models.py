@@ -231,6 +231,22 @@ def test_bert_generate_images_ids_bit_exact_vs_oracle_on_gpu(name):
     assert torch.equal(seq2, seq2_o)
     n = spec.image_seq_len
     assert torch.equal(seq2.view(B, -1)[:, :n], seq.view(B, -1)[:, -n:])
+    # temporal interpolation (visualize_long, utils_train.py:1378-1431): the first half of the previous codes becomes every
+    # other frame of the next clip, the frames in between are predicted
+    if spec.num_targets % 2 == 0:
+        Ttot = spec.target_seq_len
+        prev = seq.view(B, Ttot)
+        preserve = torch.full_like(prev, spec.MASK)
+        preserve[:, : Ttot // 2] = prev[:, : Ttot // 2]
+        torch.manual_seed(6)
+        _, _, seq3 = model.generate_images(text, visual=visual, mask_predict_steps=4, dynamic=False, preserve=preserve,
+                                           t_overlap=1, long_mode="interp")
+        torch.manual_seed(6)
+        _, seq3_o = O.bert_generate_images(spec, sd_dev, text, visual, steps=4, dynamic=False, preserve=preserve, t_overlap=1,
+                                           long_mode="interp")
+        assert torch.equal(seq3, seq3_o)
+        kept = seq3.view(B, spec.num_targets, n)[:, ::2]
+        assert torch.equal(kept, prev.view(B, spec.num_targets, n)[:, : spec.num_targets // 2])
 
 
 def test_bert_batched_sampler_is_valid_and_seeded():
