@@ -101,36 +101,33 @@ struct EpiArgs {
 template <int CPG>
 __device__ __forceinline__ void gn_chunk_partials(const float (&o)[32], float* dst, int lane) {
   constexpr int NG = 32 / CPG;
-  float s[NG], m2[NG];
+  constexpr float n = 32.f * CPG;
+  // ONE butterfly: sums of (x - K) and (x - K)^2 around a shift K taken from the slab itself (lane 0's first channel of the
+  // group), so that M2 = sum (x-K)^2 - (sum (x-K))^2 / n only cancels against the slab's own spread
+  float kk[NG], s[NG], q2[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    float a = 0.f;
-#pragma unroll
-    for (int c = 0; c < CPG; ++c) a += o[g * CPG + c];
-    s[g] = a;
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-    for (int g = 0; g < NG; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], off);
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const float mu = s[g] * (1.f / (32 * CPG));
-    float b = 0.f;
+    kk[g] = __shfl_sync(0xffffffffu, o[g * CPG], 0);
+    float a = 0.f, b2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CPG; ++c) {
-      const float d = o[g * CPG + c] - mu;
-      b = fmaf(d, d, b);
+      const float d = o[g * CPG + c] - kk[g];
+      a += d;
+      b2 = fmaf(d, d, b2);
     }
-    m2[g] = b;
+    s[g] = a; q2[g] = b2;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
-    for (int g = 0; g < NG; ++g) m2[g] += __shfl_xor_sync(0xffffffffu, m2[g], off);
+    for (int g = 0; g < NG; ++g) {
+      s[g] += __shfl_xor_sync(0xffffffffu, s[g], off);
+      q2[g] += __shfl_xor_sync(0xffffffffu, q2[g], off);
+    }
   if (lane == 0) {
 #pragma unroll
-    for (int g = 0; g < NG; ++g) *reinterpret_cast<float2*>(dst + 2 * g) = make_float2(s[g], m2[g]);
+    for (int g = 0; g < NG; ++g)
+      *reinterpret_cast<float2*>(dst + 2 * g) = make_float2(fmaf(n, kk[g], s[g]), fmaxf(q2[g] - s[g] * s[g] * (1.f / n), 0.f));
   }
 }
 
